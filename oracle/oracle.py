@@ -1,0 +1,186 @@
+"""ctypes/numpy front-end of the C oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product package never does.  Function names follow
+the reference's (nets/idetect.py, nets/iaux_detect.py, nets/ibin.py, detect.py,
+utils/bbox.py); each wrapper states which C function (and thus which reference
+file:line) it drives.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB if os.path.exists(_build.LIB) and os.path.getmtime(
+            _build.LIB) >= os.path.getmtime(_build.SRC) else _build.build()
+        _LIB = C.CDLL(path)
+        _LIB.yco_nms.restype = C.c_int
+        _LIB.yco_nms_image.restype = C.c_int
+        _LIB.yco_cvt_bbox.restype = C.c_int
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t=C.c_float):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def head_level(x, w, b, ia, im, na, no):
+    """yco_head_level: ImplicitA -> 1x1 conv -> ImplicitM -> [bs,na,ny,nx,no] raw logits."""
+    x = _f32(x)
+    bs, K, H, W = x.shape
+    w = _f32(w).reshape(na * no, K)
+    b = _f32(b) if b is not None else None
+    ia = _f32(ia).reshape(-1) if ia is not None else None
+    im = _f32(im).reshape(-1) if im is not None else None
+    raw = np.empty((bs, na, H, W, no), np.float32)
+    lib().yco_head_level(_p(x), _p(w), _p(b), _p(ia), _p(im), C.c_int(bs), C.c_int(K),
+                         C.c_int(H * W), C.c_int(na), C.c_int(no), _p(raw))
+    return raw
+
+
+def head_forward(kind, params, xs, strides):
+    """Inference forward of IDetect / IAuxDetect / IBin (nets/*.py forward, eval mode).
+
+    params: dict with lists 'w','b','ia','im' (per level), 'anchors' [nl,na,2] (pixels),
+            for 'iaux' also 'w2','b2'; for 'ibin' also 'bins_w','bins_h' and 'bin_count'.
+    xs:     list of [bs,K,H,W] arrays (nl of them; 2*nl for 'iaux').
+    Returns (z [bs, sum(na*H*W), nc+5], raws list of [bs,na,ny,nx,no]).
+    For 'iaux' the aux raws are returned as a third value (the reference computes and
+    then discards them, nets/iaux_detect.py:37-38,49).
+    """
+    anchors = _f32(params["anchors"])
+    nl, na = anchors.shape[0], anchors.shape[1]
+    bs = xs[0].shape[0]
+    no = params["w"][0].shape[0] // na
+    raws = [head_level(xs[i], params["w"][i], params["b"][i], params["ia"][i],
+                       params["im"][i], na, no) for i in range(nl)]
+    rows = sum(na * r.shape[2] * r.shape[3] for r in raws)
+    if kind == "ibin":
+        len_ = params["bin_count"] + 1
+        no_out = no - 2 * len_ + 2
+    else:
+        no_out = no
+    z = np.empty((bs, rows, no_out), np.float32)
+    off = 0
+    for i, r in enumerate(raws):
+        ny, nx = r.shape[2], r.shape[3]
+        a_wh = _f32(anchors[i].reshape(-1))
+        if kind == "ibin":
+            bw, bh = _f32(params["bins_w"]), _f32(params["bins_h"])
+            assert np.array_equal(bw, bh)
+            step = np.float32(4.0 / params["bin_count"])
+            lib().yco_decode_ibin(_p(r), C.c_int(bs), C.c_int(na), C.c_int(ny), C.c_int(nx),
+                                  C.c_int(no), C.c_int(params["bin_count"]),
+                                  C.c_float(float(strides[i])), _p(a_wh), _p(bw),
+                                  C.c_float(2.0), C.c_float(float(step)), C.c_float(0.0),
+                                  C.c_float(4.0), _p(z), C.c_int(rows), C.c_int(off))
+        else:
+            lib().yco_decode_idetect(_p(r), C.c_int(bs), C.c_int(na), C.c_int(ny),
+                                     C.c_int(nx), C.c_int(no), C.c_float(float(strides[i])),
+                                     _p(a_wh), _p(z), C.c_int(rows), C.c_int(off))
+        off += na * ny * nx
+    if kind == "iaux":
+        aux = [head_level(xs[i + nl], params["w2"][i], params["b2"][i], None, None, na, no)
+               for i in range(nl)]
+        return z, raws, aux
+    return z, raws
+
+
+def decode_box(inputs, anchors, anchors_mask, num_labels, image_size=(640, 640)):
+    """detect.decode_box (detect.py:29-87) through yco_decode_box_level."""
+    anchors = np.asarray(anchors, dtype=np.float64).reshape(-1, 2)
+    outs = []
+    for i, pred in enumerate(inputs):
+        pred = _f32(pred)
+        bs, _, ny, nx = pred.shape
+        sel = np.ascontiguousarray(anchors[anchors_mask[i]].reshape(-1))
+        na = len(anchors_mask[i])
+        no = num_labels + 5
+        out = np.empty((bs, na * ny * nx, no), np.float32)
+        lib().yco_decode_box_level(_p(pred), C.c_int(bs), C.c_int(na), C.c_int(ny),
+                                   C.c_int(nx), C.c_int(no), _p(sel, C.c_double),
+                                   C.c_double(float(image_size[0])), _p(out))
+        outs.append(out)
+    return outs
+
+
+def nms(boxes, scores, thr):
+    """torchvision.ops.nms restatement (yco_nms). Returns int64 keep indices."""
+    boxes, scores = _f32(boxes).reshape(-1, 4), _f32(scores).reshape(-1)
+    keep = np.empty(max(len(scores), 1), np.int32)
+    n = lib().yco_nms(_p(boxes), _p(scores), C.c_int(len(scores)), C.c_double(float(thr)),
+                      _p(keep, C.c_int))
+    return keep[:n].astype(np.int64)
+
+
+def nms_candidates(prediction, num_classes, conf_thres=0.5, nms_thres=0.4):
+    """Device part of detect.non_max_suppression (detect.py:97-137), per image.
+
+    prediction [bs, n, 5+nc] float32 C-contiguous is modified in place (corners), as in
+    the reference.  Returns (rows list of ndarray[k,7] xyxy, idx list of ndarray[k]).
+    """
+    assert prediction.dtype == np.float32 and prediction.flags.c_contiguous
+    bs, n, no = prediction.shape
+    assert no >= 5 + num_classes
+    rows, idxs = [], []
+    for b in range(bs):
+        if no != 5 + num_classes:
+            sub = np.ascontiguousarray(prediction[b][:, :5 + num_classes])
+        else:
+            sub = prediction[b]
+        o = np.empty((n, 7), np.float32)
+        ix = np.empty(max(n, 1), np.int32)
+        k = lib().yco_nms_image(_p(sub), C.c_int(n), C.c_int(num_classes),
+                                C.c_float(float(np.float32(conf_thres))),
+                                C.c_double(float(nms_thres)), _p(o), _p(ix, C.c_int))
+        if sub is not prediction[b]:
+            prediction[b][:, :4] = sub[:, :4]
+        rows.append(o[:k].copy())
+        idxs.append(ix[:k].copy())
+    return rows, idxs
+
+
+def correct_boxes_rows(rows, input_shape, image_shape, letterbox_image):
+    """detect.py:140-142 + yolo_correct_boxes (detect.py:147-165) on [k,7] rows, in place."""
+    rows = np.ascontiguousarray(rows, np.float32)
+    lib().yco_correct_boxes(_p(rows), C.c_int(rows.shape[0]), C.c_int(int(input_shape[0])),
+                            C.c_int(int(input_shape[1])), C.c_int(int(image_shape[0])),
+                            C.c_int(int(image_shape[1])), C.c_int(1 if letterbox_image else 0))
+    return rows
+
+
+def non_max_suppression(prediction, num_classes, input_shape, image_shape, letterbox_image,
+                        conf_thres=0.5, nms_thres=0.4, return_indices=False):
+    """detect.non_max_suppression (detect.py:90-144): list of None | ndarray[k,7] (yxyx px)."""
+    rows, idxs = nms_candidates(prediction, num_classes, conf_thres, nms_thres)
+    out = [None if r.shape[0] == 0 else
+           correct_boxes_rows(r, input_shape, image_shape, letterbox_image) for r in rows]
+    return (out, idxs) if return_indices else out
+
+
+def box_iou(b1, b2):
+    b1, b2 = _f32(b1).reshape(-1, 4), _f32(b2).reshape(-1, 4)
+    out = np.empty((b1.shape[0], b2.shape[0]), np.float32)
+    lib().yco_box_iou(_p(b1), C.c_int(b1.shape[0]), _p(b2), C.c_int(b2.shape[0]), _p(out))
+    return out
+
+
+def cvt_bbox(bbox, flag):
+    bbox = _f32(bbox).reshape(-1, 4)
+    out = np.empty_like(bbox)
+    rc = lib().yco_cvt_bbox(_p(bbox), C.c_int(bbox.shape[0]), C.c_int(int(flag)), _p(out))
+    if rc != 0:
+        raise Exception()
+    return out

@@ -1,0 +1,87 @@
+"""Pin the CPU oracle (oracle/) against fixtures produced by the unmodified reference.
+
+Bit-exact where the arithmetic is IEEE-determined (layout conversions, corners,
+thresholding, NMS keep sets, letterbox undo); tolerance 2e-6 (scaled, see helpers)
+where libm/oneDNN differ by an ulp or two (1x1 conv accumulation order, expf).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from helpers import assert_close_scaled, box_scale, head_params, load
+
+RTOL_ORACLE = 2e-6
+
+
+@pytest.mark.parametrize("name,kind", [("idetect_nc80", "idetect"), ("idetect_nc1_rect", "idetect"),
+                                       ("iaux_nc80", "iaux"), ("ibin_nc80", "ibin")])
+def test_head_forward_matches_reference(name, kind):
+    fx = load(name)
+    p = head_params(fx, kind)
+    nl = p["anchors"].shape[0]
+    nx_in = 2 * nl if kind == "iaux" else nl
+    xs = [fx[f"x{i}"] for i in range(nx_in)]
+    res = orc.head_forward(kind, p, xs, fx["strides"])
+    z, raws = res[0], res[1]
+    shapes = [fx[f"raw{i}"].shape[2:4] for i in range(nl)]
+    na = p["anchors"].shape[1]
+    for i in range(nl):
+        np.testing.assert_allclose(raws[i], fx[f"raw{i}"], rtol=0, atol=RTOL_ORACLE, err_msg=f"raw{i}")
+    assert z.shape == fx["z"].shape
+    scale = box_scale(p["anchors"], fx["strides"], shapes, na, z.shape[-1])
+    assert_close_scaled(z, fx["z"], scale, RTOL_ORACLE, name)
+    if kind == "iaux":
+        for i in range(nl):
+            np.testing.assert_allclose(res[2][i], fx[f"aux{i}"], rtol=0, atol=RTOL_ORACLE)
+
+
+def test_decode_box_variant_a():
+    fx = load("variant_a")
+    outs = orc.decode_box([fx[f"conv{i}"] for i in range(3)], fx["anchors"], fx["mask"].tolist(),
+                          int(fx["nc"]), tuple(fx["image_size"]))
+    for i in range(3):
+        np.testing.assert_allclose(outs[i], fx[f"out{i}"], rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize("name", ["nms_clustered_lb", "nms_clustered_nolb", "nms_lowconf",
+                                  "nms_with_none", "nms_nc1", "nms_thr_round"])
+def test_non_max_suppression_bit_exact(name):
+    fx = load(name)
+    pred = fx["pred"].copy()
+    out, idx = orc.non_max_suppression(pred, int(fx["nc"]), tuple(fx["input_shape"]), tuple(fx["image_shape"]),
+                                       bool(fx["letterbox"]), float(fx["conf"]), float(fx["iou"]),
+                                       return_indices=True)
+    # in-place corner write-back, detect.py:98-103
+    assert np.array_equal(pred[..., :4], fx["corners"])
+    counts = [0 if o is None else o.shape[0] for o in out]
+    assert counts == fx["counts"].tolist()
+    assert np.array_equal(np.concatenate(idx), fx["keep_idx"])
+    rows = [o for o in out if o is not None]
+    got = np.concatenate(rows, 0) if rows else np.zeros((0, 7), np.float32)
+    assert np.array_equal(got[:, 4:], fx["rows"][:, 4:])
+    assert np.array_equal(got[:, :4], fx["rows"][:, :4].astype(np.float32))
+    for o, c in zip(out, counts):
+        assert (o is None) == (c == 0)
+
+
+def test_nms_probes():
+    fx = load("nms_probes")
+    for k in ("third", "ties", "zero_area"):
+        for tn, thr in (("a", 1 / 3), ("b", float(np.float32(1 / 3))), ("c", 0.5)):
+            keep = orc.nms(fx[k + "_boxes"], fx[k + "_scores"], thr)
+            assert np.array_equal(keep, fx[f"{k}_keep_{tn}"]), (k, tn)
+    for thr in (0.3, 0.45, 0.65):
+        assert np.array_equal(orc.nms(fx["rand_boxes"], fx["rand_scores"], thr), fx[f"rand_keep_{thr}"])
+
+
+def test_bbox_known_answers():
+    """utils/bbox.py:207-225, the reference's only known-answer data."""
+    fx = load("bbox_kat")
+    expect = {0: [1, 3, 2, 5], 1: [1.5, 4, 1, 2]}
+    assert orc.cvt_bbox(fx["xxyy"], 0).tolist() == [expect[0]]
+    assert orc.cvt_bbox(fx["xxyy"], 1).tolist() == [expect[1]]
+    for f in range(6):
+        assert np.array_equal(orc.cvt_bbox(fx["boxes"], f), fx[f"out_{f}"]), f
+    with pytest.raises(Exception):
+        orc.cvt_bbox(fx["boxes"], 6)
+    assert np.array_equal(orc.box_iou(fx["iou_b1"], fx["iou_b2"]), fx["iou"])
