@@ -1,0 +1,144 @@
+/*
+ * yc_b200.h -- C ABI of the B200-native detection post-backbone path.
+ *
+ * Drop-in boundary for xin-pu/yolo-continuous (reference paths relative to its
+ * checkout).  The reference has no FFI of its own (100 % Python); these entry points
+ * are what a binding for the path would call.  Every function takes plain pointers and
+ * sizes, launches on the caller's stream, never synchronises the host unless stated,
+ * and returns 0 on success or a negative yc_status; yc_last_error() gives the text.
+ * All pointers are DEVICE pointers unless the name ends in _host.
+ */
+#ifndef YC_B200_H
+#define YC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define YC_API __attribute__((visibility("default")))
+#else
+#define YC_API
+#endif
+
+#define YC_MAX_LEVELS 4
+#define YC_MAX_ANCHORS 4
+
+typedef void *yc_stream_t; /* cudaStream_t */
+
+enum yc_status {
+    YC_OK = 0,
+    YC_ERR_INVALID = -1,     /* bad argument */
+    YC_ERR_UNSUPPORTED = -2, /* shape / dtype not supported by this build */
+    YC_ERR_CUDA = -3,        /* CUDA runtime / driver error */
+    YC_ERR_WORKSPACE = -4    /* workspace too small */
+};
+
+enum yc_dtype { YC_F32 = 0, YC_BF16 = 1 };
+
+/* decode performed by the head epilogue */
+enum yc_head_kind {
+    YC_HEAD_IDETECT = 0, /* nets/idetect.py:40-43 (also IAuxDetect lead branch, nets/iaux_detect.py:44-47) */
+    YC_HEAD_IBIN = 1,    /* nets/ibin.py:56-72 + losses/sigmoid_bin.py:49-63 */
+    YC_HEAD_RAW = 2      /* conv (+implicit) + permute only: training output, IAuxDetect m2 branch
+                            (nets/iaux_detect.py:37-38) */
+};
+
+/* which kernel family runs the 1x1 conv */
+enum yc_head_path {
+    YC_PATH_AUTO = 0,    /* tcgen05 when the shape allows it, else generic */
+    YC_PATH_TCGEN05 = 1, /* sm_100a tcgen05/TMEM/TMA kernel; YC_ERR_UNSUPPORTED if the shape does not fit */
+    YC_PATH_GENERIC = 2  /* any-shape FFMA kernel (exact binary32 accumulation) */
+};
+
+YC_API const char *yc_last_error(void);
+YC_API int yc_version(void);
+/* 0 when device `dev` is an sm_100 part this library can run on. */
+YC_API int yc_device_check(int dev);
+
+/* ------------------------------------------------------------------------------------------
+ * Head parameters.  Replaces the parameter handling of IDetect/IAuxDetect/IBin
+ * (nets/idetect.py:21-24, nets/common.py:416-439): ImplicitA is folded into the bias
+ * (b' = b + W.ia, binary64 accumulation), ImplicitM stays a per-channel epilogue scale.
+ * yc_head_pack writes one blob per level:
+ *   [bias2 f32 Npad][scale f32 Npad][scale_split f32 Npad][w32 f32 N*K]
+ *   [w_hi f16 Npad*K][w_lo f16 Npad*K][w_bf16 Npad*K]          (Npad = N rounded up to 16)
+ * W [N,K] f32 row-major (Conv2d weight [N,K,1,1]); bias [N] or NULL; ia [K] or NULL; im [N] or NULL.
+ */
+YC_API size_t yc_head_pack_bytes(int N, int K);
+YC_API int yc_head_pack(const float *W, const float *bias, const float *ia, const float *im, int N, int K,
+                 void *blob, yc_stream_t stream);
+
+typedef struct yc_head_level {
+    const void *x;     /* [bs, K, H, W] NCHW feature map, dtype = yc_head_desc.x_dtype */
+    const void *blob;  /* from yc_head_pack */
+    float *raw;        /* optional [bs, na, H, W, no] pre-sigmoid output (forward()'s list `x`), or NULL */
+    int32_t K, H, W;
+    float stride;                         /* IDetect.stride[i] */
+    float anchor_wh[YC_MAX_ANCHORS * 2];  /* anchor_grid[i] in pixels, nets/idetect.py:18-20 */
+} yc_head_level;
+
+typedef struct yc_head_desc {
+    int32_t kind;      /* yc_head_kind */
+    int32_t path;      /* yc_head_path */
+    int32_t x_dtype;   /* yc_dtype of the feature maps: YC_F32 -> fp32-grade result (fp16 hi/lo split
+                          on tensor cores, or exact FFMA on the generic path); YC_BF16 -> bf16 MMA */
+    int32_t nl, na, no; /* levels, anchors per level, conv outputs per anchor (85; IBin 127) */
+    int32_t bin_count;  /* IBin only (21) */
+    int32_t bs;
+    yc_head_level level[YC_MAX_LEVELS];
+    float *z;           /* [bs, sum(na*H*W), no_out] decoded rows (no_out = no, IBin: no - 2*(bin_count+1) + 2),
+                           NULL for YC_HEAD_RAW */
+    const float *bins;  /* IBin: device [bin_count] (SigmoidBin.bins buffer) */
+} yc_head_desc;
+
+/* IDetect/IAuxDetect/IBin.forward (eval and train) for all levels in one call.
+ * Replaces nets/idetect.py:26-45, nets/iaux_detect.py:27-49, nets/ibin.py:35-74. */
+YC_API int yc_head_forward(const yc_head_desc *desc, yc_stream_t stream);
+
+/* Variant A decode: detect.decode_box, detect.py:29-87, one level.
+ * conv [bs, na*no, ny, nx] f32 -> out [bs, na*ny*nx, no] normalised xywh + sigmoid scores. */
+YC_API int yc_decode_box(const float *conv, int bs, int na, int no, int ny, int nx, const float *anchor_wh_scaled_host,
+                  float *out, yc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Threshold + compaction + batched per-class NMS (+ letterbox undo).
+ * Replaces detect.non_max_suppression, detect.py:90-144 (utils/bbox.py:121-198) and
+ * torchvision.ops.nms at detect.py:133, for a whole batch without host round trips.
+ */
+typedef struct yc_nms_params {
+    int32_t bs, rows, row_stride; /* pred [bs, rows, row_stride] f32, row = cx,cy,w,h,obj,cls[nc] */
+    int32_t nc;
+    float conf_thres;             /* compared in binary32, as torch does (detect.py:111) */
+    double nms_thres;             /* compared in binary64 against the binary32 IoU, as torchvision does */
+    int32_t write_corners;        /* 1: overwrite pred[..., :4] with x1,y1,x2,y2 (detect.py:98-103) */
+    int32_t correct_boxes;        /* 1: apply yolo_correct_boxes (detect.py:147-165): rows become y1,x1,y2,x2 px */
+    int32_t letterbox;
+    int32_t input_h, input_w;
+    const int32_t *image_hw;      /* device [bs,2] original image h,w (or [1,2] with image_hw_stride 0) */
+    int32_t image_hw_stride;      /* 2 or 0 */
+} yc_nms_params;
+
+YC_API size_t yc_nms_workspace_bytes(int bs, int rows, int nc);
+/* out_rows [bs*rows, 7] capacity (dense: image b's detections start at out_offsets[b]),
+ * out_idx [bs*rows] original row index of each kept detection, out_counts [bs], out_offsets [bs+1]. */
+YC_API int yc_nms_batched(float *pred, const yc_nms_params *p, void *workspace, size_t workspace_bytes, float *out_rows,
+                   int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets, yc_stream_t stream);
+
+/* torchvision.ops.nms drop-in for one box set (detect.py:133): boxes [n,4] xyxy, scores [n].
+ * keep [n] receives kept indices in score order, *keep_count_dev their number. workspace from
+ * yc_nms_workspace_bytes(1, n, 1). */
+YC_API int yc_nms_single(const float *boxes, const float *scores, int n, double thr, void *workspace, size_t workspace_bytes,
+                  int32_t *keep, int32_t *keep_count_dev, yc_stream_t stream);
+
+/* utils/bbox.py:62-72 box_iou and :29-59 cvt_bbox on device. */
+YC_API int yc_box_iou(const float *b1, int n, const float *b2, int m, float *out, yc_stream_t stream);
+YC_API int yc_cvt_bbox(const float *in, int n, int flag, float *out, yc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YC_B200_H */

@@ -1,0 +1,115 @@
+"""CPU-side checks of the C-ABI boundary: the library loads and exports exactly what
+include/yc_b200.h declares; descriptor structs match the header layout; host-side logic."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "yc_b200.h")).read()
+    return sorted(set(re.findall(r"YC_API\s+[\w\s\*]+?\b(yc_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from yolo_continuous_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(_lib.lib, n), n
+    assert sorted(_lib.EXPORTS) == names
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
+    assert exported == names  # nothing else leaks out of the shared object
+    assert _lib.lib.yc_version() == 100
+
+
+def test_struct_layout_matches_header(tmp_path):
+    """Compile a tiny C program against the header and compare sizeof/offsetof with ctypes."""
+    from yolo_continuous_b200 import _lib
+    src = tmp_path / "probe.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "yc_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(yc_head_level), sizeof(yc_head_desc), sizeof(yc_nms_params),
+         offsetof(yc_head_level, anchor_wh), offsetof(yc_head_desc, level), offsetof(yc_head_desc, z),
+         offsetof(yc_head_desc, bins), offsetof(yc_nms_params, nms_thres), offsetof(yc_nms_params, image_hw));
+  return 0; }''')
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    want = [C.sizeof(_lib.HeadLevel), C.sizeof(_lib.HeadDesc), C.sizeof(_lib.NmsParams),
+            _lib.HeadLevel.anchor_wh.offset, _lib.HeadDesc.level.offset, _lib.HeadDesc.z.offset,
+            _lib.HeadDesc.bins.offset, _lib.NmsParams.nms_thres.offset, _lib.NmsParams.image_hw.offset]
+    assert got == want
+
+
+def test_size_queries_need_no_gpu():
+    from yolo_continuous_b200 import _lib
+    assert _lib.lib.yc_head_pack_bytes(255, 256) > 255 * 256 * 4
+    assert _lib.lib.yc_head_pack_bytes(0, 256) == 0
+    assert _lib.lib.yc_nms_workspace_bytes(64, 25200, 80) > 64 * 25200 * 60
+    assert _lib.lib.yc_nms_workspace_bytes(0, 1, 1) == 0
+
+
+def test_product_refuses_cpu_tensors():
+    import torch
+    from yolo_continuous_b200 import _lib, detect
+    from yolo_continuous_b200.nets import IDetect
+    from yolo_continuous_b200.utils import bbox
+    with pytest.raises(_lib.YcError):
+        detect.non_max_suppression(torch.zeros(1, 8, 85), 80, (640, 640), (640, 640), True)
+    with pytest.raises(_lib.YcError):
+        bbox.box_iou(torch.zeros(2, 4), torch.zeros(3, 4))
+    head = IDetect(2, [[10, 13, 16, 30, 33, 23]], (8,)).eval()
+    head.stride = torch.tensor([8.0])
+    with pytest.raises(_lib.YcError):
+        head([torch.zeros(1, 8, 4, 4)])
+
+
+def test_state_dict_keys_match_reference_fixtures():
+    """Checkpoint compatibility: same keys and shapes as the reference heads."""
+    import torch
+    from helpers import load
+    from yolo_continuous_b200.nets import IAuxDetect, IBin, IDetect
+    coco = [[12, 16, 19, 36, 40, 28], [36, 75, 76, 55, 72, 146], [142, 110, 192, 243, 459, 401]]
+    for cls, name, ch in ((IDetect, "idetect_nc80", (16, 32, 64)), (IAuxDetect, "iaux_nc80", (16, 32, 64) * 2),
+                          (IBin, "ibin_nc80", (16, 32, 64))):
+        fx = load(name)
+        ref = {k[4:].replace("__", "."): v.shape for k, v in fx.items() if k.startswith("sd__")}
+        head = cls(80, coco, ch)
+        mine = {k: tuple(v.shape) for k, v in head.state_dict().items()}
+        assert mine == {k: tuple(s) for k, s in ref.items()}, name
+        head.load_state_dict({k[4:].replace("__", "."): torch.from_numpy(v) for k, v in fx.items()
+                              if k.startswith("sd__")})
+
+
+def test_host_utils_match_reference_known_answers():
+    from helpers import load
+    from yolo_continuous_b200.utils import bbox
+    fx = load("bbox_kat")
+    for f in bbox.CvtFlag:
+        assert np.array_equal(bbox.cvt_bbox(fx["boxes"].copy(), f), fx[f"out_{f.value}"])
+    assert np.array_equal(bbox.make_grid(5, 3).numpy(), fx["grid_5_3"])
+    with pytest.raises(Exception):
+        bbox.cvt_bbox(fx["boxes"], type("F", (), {"value": 9})())
+
+
+def test_yolo_correct_boxes_host_matches_oracle():
+    from oracle import oracle as orc
+    from yolo_continuous_b200 import detect
+    g = np.random.default_rng(0)
+    rows = np.zeros((50, 7), np.float32)
+    rows[:, :2] = g.uniform(0, 0.5, (50, 2)); rows[:, 2:4] = rows[:, :2] + g.uniform(0.01, 0.5, (50, 2))
+    for lb, shp in ((True, (512, 773)), (False, (480, 640)), (True, (1080, 1920))):
+        want = orc.correct_boxes_rows(rows.copy(), (640, 640), shp, lb)[:, :4]
+        xy, wh = (rows[:, 0:2] + rows[:, 2:4]) / 2, rows[:, 2:4] - rows[:, 0:2]
+        got = detect.yolo_correct_boxes(xy, wh, (640, 640), np.array(shp), lb).astype(np.float32)
+        assert np.array_equal(got, want)

@@ -1,0 +1,326 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and against the
+golden fixtures generated from the unmodified reference.
+
+Tolerances (north_star): decoded boxes/scores |a-b| <= rtol*max(|ref|, s)
+with s = stride (xy), anchor (wh), 1 (scores); rtol = 1e-5 for float32 feature maps and 1e-3 for
+bfloat16 (bf16-representable inputs fed to both sides).  Threshold / NMS results are bit-exact on
+identical inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close_scaled, box_scale, head_params, load
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+COCO = [[12, 16, 19, 36, 40, 28], [36, 75, 76, 55, 72, 146], [142, 110, 192, 243, 459, 401]]
+TINY = [[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]]
+RTOL_F32, RTOL_BF16 = 1e-5, 1e-3
+DEV = "cuda:0"
+
+
+def _heads():
+    from yolo_continuous_b200.nets import IAuxDetect, IBin, IDetect
+    return {"idetect": IDetect, "iaux": IAuxDetect, "ibin": IBin}
+
+
+def build_head(kind, fx, anchors, ch, path=None):
+    from yolo_continuous_b200 import _lib
+    head = _heads()[kind](int(fx["nc"]), anchors, ch).eval()
+    head.load_state_dict({k[4:].replace("__", "."): torch.from_numpy(v) for k, v in fx.items() if k.startswith("sd__")})
+    head.stride = torch.tensor(fx["strides"])
+    head = head.to(DEV)
+    if path is not None:
+        head.head_path = {"generic": _lib.YC_PATH_GENERIC, "tcgen05": _lib.YC_PATH_TCGEN05, "auto": _lib.YC_PATH_AUTO}[path]
+    return head
+
+
+CASES = [("idetect_nc80", "idetect", COCO, (16, 32, 64)), ("idetect_nc1_rect", "idetect", TINY, (8, 16, 32)),
+         ("iaux_nc80", "iaux", COCO, (16, 32, 64, 16, 32, 64)), ("ibin_nc80", "ibin", COCO, (16, 32, 64))]
+
+
+@pytest.mark.parametrize("name,kind,anchors,ch", CASES)
+def test_head_forward_vs_golden_fp32(name, kind, anchors, ch):
+    """Eval forward == the reference's (z, x) on the reference's own inputs and weights."""
+    fx = load(name)
+    head = build_head(kind, fx, anchors, ch, "auto")
+    nl = head.nl
+    xs = [torch.from_numpy(fx[f"x{i}"]).to(DEV) for i in range(len(ch))]
+    lst = list(xs)
+    z, raws = head(lst)
+    assert z.dtype == torch.float32 and z.is_contiguous()
+    shapes = [fx[f"raw{i}"].shape[2:4] for i in range(nl)]
+    p = head_params(fx, kind)
+    scale = box_scale(p["anchors"], fx["strides"], shapes, head.na, z.shape[-1])
+    assert_close_scaled(z.cpu().numpy(), fx["z"], scale, RTOL_F32, name)
+    assert len(raws) == nl
+    for i in range(nl):
+        np.testing.assert_allclose(raws[i].cpu().numpy(), fx[f"raw{i}"], rtol=0, atol=1e-5)
+        assert lst[i] is raws[i]  # the caller's list is updated in place (nets/idetect.py:31-34)
+        assert tuple(head.grid[i].shape) == (1, 1) + tuple(shapes[i]) + (2,)
+    if kind == "iaux":
+        for i in range(nl):
+            np.testing.assert_allclose(lst[i + nl].cpu().numpy(), fx[f"aux{i}"], rtol=0, atol=1e-5)
+    # train mode returns the raw maps only
+    head.train()
+    tr = head([x.clone() for x in xs])
+    for i in range(nl):
+        np.testing.assert_allclose(tr[i].cpu().numpy(), fx[f"raw{i}"], rtol=0, atol=1e-5)
+
+
+def test_head_stride_unset_raises_like_reference():
+    from yolo_continuous_b200.nets import IDetect
+    head = IDetect(2, [[10, 13, 16, 30, 33, 23]], (8,)).eval().to(DEV)
+    with pytest.raises(TypeError):
+        head([torch.zeros(1, 8, 4, 4, device=DEV)])
+
+
+def _random_head_case(kind, nc, ch, shapes, bs, seed, dtype):
+    """Seeded synthetic weights (conv N(0,.02), im N(1,.02), bias shift) and feature maps."""
+    from yolo_continuous_b200.nets import IAuxDetect, IBin, IDetect
+    g = torch.Generator().manual_seed(seed)
+    cls = {"idetect": IDetect, "iaux": IAuxDetect, "ibin": IBin}[kind]
+    head = cls(nc, COCO, ch).eval()
+    with torch.no_grad():
+        for n_, p_ in head.named_parameters():
+            if n_.endswith("weight"):
+                p_.copy_(torch.randn(p_.shape, generator=g) * 0.02)
+            elif n_.startswith("im."):
+                p_.copy_(1.0 + torch.randn(p_.shape, generator=g) * 0.02)
+            elif n_.startswith("ia."):
+                p_.copy_(torch.randn(p_.shape, generator=g) * 0.02)
+            elif n_.endswith("bias"):
+                p_.copy_(torch.randn(p_.shape, generator=g) * 0.5 - 1.0)
+    head.stride = torch.tensor([8.0, 16.0, 32.0])
+    xs = [torch.randn(bs, c, h, w, generator=g) for c, (h, w) in zip(ch, shapes)]
+    if dtype == torch.bfloat16:
+        xs = [x.to(torch.bfloat16) for x in xs]
+    return head, xs
+
+
+def _oracle_params(head, kind, bf16):
+    def w_(conv):
+        w = conv.weight.detach()[:, :, 0, 0]
+        return (w.to(torch.bfloat16).float() if bf16 else w).numpy()
+    nl = head.nl
+    p = {"anchors": head.anchor_grid.detach().cpu().reshape(nl, -1, 2).numpy(),
+         "w": [w_(head.m[i]) for i in range(nl)], "b": [head.m[i].bias.detach().numpy() for i in range(nl)],
+         "ia": [head.ia[i].implicit.detach().reshape(-1).numpy() for i in range(nl)],
+         "im": [head.im[i].implicit.detach().reshape(-1).numpy() for i in range(nl)]}
+    if kind == "iaux":
+        p["w2"] = [w_(head.m2[i]) for i in range(nl)]
+        p["b2"] = [head.m2[i].bias.detach().numpy() for i in range(nl)]
+    if kind == "ibin":
+        p["bins_w"] = head.w_bin_sigmoid.bins.numpy()
+        p["bins_h"] = head.h_bin_sigmoid.bins.numpy()
+        p["bin_count"] = head.bin_count
+    return p
+
+
+@pytest.mark.parametrize("path", ["generic", "auto"])
+@pytest.mark.parametrize("kind,dtype,rtol", [("idetect", torch.float32, RTOL_F32), ("idetect", torch.bfloat16, RTOL_BF16),
+                                             ("ibin", torch.float32, RTOL_F32), ("iaux", torch.bfloat16, RTOL_BF16)])
+def test_head_forward_vs_oracle_coco_channels(kind, dtype, rtol, path):
+    """COCO-shaped channel counts (256/512/1024) on a small spatial grid, so the oracle finishes in
+    seconds; exercises K-loop depth and, on `auto`, the tcgen05 kernel with ragged pixel tiles."""
+    from yolo_continuous_b200 import _lib
+    ch = (256, 512, 1024) * (2 if kind == "iaux" else 1)
+    shapes = [(12, 20), (6, 10), (3, 5)] * (2 if kind == "iaux" else 1)
+    head, xs = _random_head_case(kind, 80, ch, shapes, 2, 7, dtype)
+    bf16 = dtype == torch.bfloat16
+    p = _oracle_params(head, kind, bf16)
+    res = orc.head_forward(kind, p, [x.float().numpy() for x in xs], [8.0, 16.0, 32.0])
+    head = head.to(DEV)
+    head.head_path = _lib.YC_PATH_GENERIC if path == "generic" else _lib.YC_PATH_AUTO
+    z, raws = head([x.to(DEV) for x in xs])
+    scale = box_scale(p["anchors"], [8.0, 16.0, 32.0], shapes[:3], head.na, z.shape[-1])
+    zc = z.cpu().numpy()
+    if kind == "ibin":
+        # rows whose two best bins tie within float noise may legitimately pick either (argmax on
+        # sigmoids, losses/sigmoid_bin.py:54); exclude them from the w/h comparison
+        bad = np.abs(zc[..., 2:4] - res[0][..., 2:4]) > rtol * np.maximum(np.abs(res[0][..., 2:4]), scale[..., 2:4])
+        assert bad.mean() < 1e-3
+        zc[..., 2:4] = np.where(bad, res[0][..., 2:4], zc[..., 2:4])
+    assert_close_scaled(zc, res[0], scale, rtol, f"{kind}/{dtype}/{path}")
+    for i in range(head.nl):
+        np.testing.assert_allclose(raws[i].cpu().numpy(), res[1][i], rtol=0, atol=rtol * 4)
+
+
+def test_decode_box_variant_a_vs_golden():
+    from yolo_continuous_b200 import detect
+    fx = load("variant_a")
+    outs = detect.decode_box([torch.from_numpy(fx[f"conv{i}"]).to(DEV) for i in range(3)], fx["anchors"],
+                             fx["mask"].tolist(), int(fx["nc"]), tuple(fx["image_size"]))
+    for i in range(3):
+        np.testing.assert_allclose(outs[i].cpu().numpy(), fx[f"out{i}"], rtol=1e-5, atol=1e-6)
+
+
+NMS_FIXTURES = ["nms_clustered_lb", "nms_clustered_nolb", "nms_lowconf", "nms_with_none", "nms_nc1", "nms_thr_round"]
+
+
+@pytest.mark.parametrize("name", NMS_FIXTURES)
+def test_nms_vs_golden_bit_exact(name):
+    from yolo_continuous_b200 import detect
+    fx = load(name)
+    pred = torch.from_numpy(fx["pred"].copy()).to(DEV)
+    out, idx = detect.non_max_suppression(pred, int(fx["nc"]), tuple(fx["input_shape"]), tuple(fx["image_shape"]),
+                                          bool(fx["letterbox"]), float(fx["conf"]), float(fx["iou"]),
+                                          return_indices=True)
+    assert np.array_equal(pred[..., :4].cpu().numpy(), fx["corners"])  # in-place corners, detect.py:98-103
+    counts = [0 if o is None else o.shape[0] for o in out]
+    assert counts == fx["counts"].tolist()
+    assert np.array_equal(np.concatenate(idx), fx["keep_idx"])
+    rows = [o for o in out if o is not None]
+    got = np.concatenate(rows, 0) if rows else np.zeros((0, 7), np.float32)
+    assert got.dtype == np.float32
+    assert np.array_equal(got, fx["rows"].astype(np.float32))
+    for o, c in zip(out, counts):
+        assert (o is None) == (c == 0)
+
+
+def _synthetic_pred(bs, rows, nc, seed, skew=False, dense=False):
+    g = np.random.default_rng(seed)
+    p = np.empty((bs, rows, 5 + nc), np.float32)
+    n_obj = 30
+    for b in range(bs):
+        ctr, size = g.uniform(0.1, 0.9, (n_obj, 2)), g.uniform(0.03, 0.35, (n_obj, 2))
+        which = g.integers(0, n_obj, rows)
+        fg = g.uniform(size=rows) < (0.9 if dense else 0.3)
+        p[b, :, 0:2] = np.where(fg[:, None], ctr[which] + g.normal(0, 0.01, (rows, 2)), g.uniform(0, 1, (rows, 2)))
+        p[b, :, 2:4] = np.where(fg[:, None], size[which] * g.uniform(0.8, 1.25, (rows, 2)), g.uniform(0.01, 0.1, (rows, 2)))
+        p[b, :, 4] = 1 / (1 + np.exp(-np.where(fg, g.normal(1.0, 1.5, rows), g.normal(-4, 1.5, rows))))
+        cls = 1 / (1 + np.exp(-g.normal(-2.5, 1.0, (rows, nc))))
+        hot = np.zeros(rows, np.int64) if skew else g.integers(0, nc, n_obj)[which]
+        cls[np.arange(rows), hot] = 1 / (1 + np.exp(-g.normal(2.5, 1.0, rows)))
+        p[b, :, 5:] = cls
+    p[0, 5] = p[0, 2]            # duplicated row: equal score, equal box
+    p[0, 9, 4:] = p[0, 2, 4:]    # equal score, different box
+    return p
+
+
+@pytest.mark.parametrize("bs,rows,nc,conf,iou,kw", [
+    (2, 25200, 80, 0.25, 0.45, {}),                       # C2-shaped
+    (2, 25200, 80, 0.001, 0.65, {}),                      # C3-shaped: ~all rows are candidates
+    (1, 6000, 80, 0.001, 0.65, {"skew": True, "dense": True}),  # one class owns everything: global-memory sort, kept spill
+    (3, 1000, 1, 0.3, 0.3, {}),                           # C1-shaped, single class
+    (1, 37, 3, 0.0, 0.5, {}),                             # ragged tile, every row passes
+    (2, 300, 80, 0.999999, 0.5, {}),                      # nothing passes -> None for every image
+])
+def test_nms_vs_oracle_bit_exact(bs, rows, nc, conf, iou, kw):
+    from yolo_continuous_b200 import detect
+    pred = _synthetic_pred(bs, rows, nc, 3, **kw)
+    want, widx = orc.non_max_suppression(pred.copy(), nc, (640, 640), (512, 773), True, conf, iou, return_indices=True)
+    dev = torch.from_numpy(pred).to(DEV)
+    got, gidx = detect.non_max_suppression(dev, nc, (640, 640), (512, 773), True, conf, iou, return_indices=True)
+    for b in range(bs):
+        assert (got[b] is None) == (want[b] is None), b
+        assert np.array_equal(gidx[b], widx[b].astype(np.int64)), (b, len(gidx[b]), len(widx[b]))
+        if want[b] is not None:
+            assert np.array_equal(got[b], want[b]), b
+
+
+def test_nms_single_matches_torchvision_semantics():
+    from yolo_continuous_b200 import detect
+    fx = load("nms_probes")
+    for k in ("third", "ties", "zero_area"):
+        for tn, thr in (("a", 1 / 3), ("b", float(np.float32(1 / 3))), ("c", 0.5)):
+            keep = detect.nms(torch.from_numpy(fx[k + "_boxes"]).to(DEV), torch.from_numpy(fx[k + "_scores"]).to(DEV), thr)
+            assert keep.dtype == torch.int64
+            assert np.array_equal(keep.cpu().numpy(), fx[f"{k}_keep_{tn}"]), (k, tn)
+    for thr in (0.3, 0.45, 0.65):
+        keep = detect.nms(torch.from_numpy(fx["rand_boxes"]).to(DEV), torch.from_numpy(fx["rand_scores"]).to(DEV), thr)
+        assert np.array_equal(keep.cpu().numpy(), fx[f"rand_keep_{thr}"])
+    g = np.random.default_rng(1)
+    n = 9000  # > SORT_SMEM: in-place global-memory sort; > KEPT_SMEM kept boxes
+    b = g.uniform(0, 1, (n, 4)).astype(np.float32) * 0.9
+    b[:, 2:] = b[:, :2] + g.uniform(0.005, 0.05, (n, 2)).astype(np.float32)
+    s = g.uniform(0, 1, n).astype(np.float32)
+    s[100:200] = s[0]
+    keep = detect.nms(torch.from_numpy(b).to(DEV), torch.from_numpy(s).to(DEV), 0.3)
+    assert np.array_equal(keep.cpu().numpy(), orc.nms(b, s, 0.3))
+    assert detect.nms(torch.zeros(0, 4, device=DEV), torch.zeros(0, device=DEV), 0.5).numel() == 0
+
+
+def test_nms_properties_full_size():
+    """Size-independent properties at the mAP-eval stress size (bs 8 of config C3's 256):
+    output ordered by (class asc, score desc); no kept same-class pair overlaps above the threshold;
+    every dropped candidate is covered by a kept, higher-priority, same-class box; idempotence."""
+    from yolo_continuous_b200 import detect
+    from yolo_continuous_b200.utils import bbox
+    bs, rows, nc, conf, iou = 8, 25200, 80, 0.001, 0.65
+    pred = torch.from_numpy(_synthetic_pred(bs, rows, nc, 11, dense=True)).to(DEV)
+    rows_d, idx_d, counts, offsets = detect.nms_device(pred, nc, conf, iou)
+    off = offsets.cpu().numpy()
+    assert off[0] == 0 and np.array_equal(np.diff(off), counts.cpu().numpy())
+    for b in range(bs):
+        det = rows_d[off[b]:off[b + 1]]
+        kidx = idx_d[off[b]:off[b + 1]].long()
+        assert torch.equal(det[:, :4], pred[b, kidx, :4])          # rows are the kept candidates' corners
+        cls, score = det[:, 6], det[:, 4] * det[:, 5]
+        order_ok = (cls[1:] > cls[:-1]) | ((cls[1:] == cls[:-1]) & (score[1:] <= score[:-1]))
+        assert bool(order_ok.all())
+        ious = bbox.box_iou(det[:, :4].contiguous(), det[:, :4].contiguous())
+        same = cls[:, None] == cls[None, :]
+        upper = torch.triu(torch.ones_like(ious, dtype=torch.bool), 1)
+        assert not bool(((ious > iou) & same & upper).any())
+        # coverage of dropped candidates
+        cc, cp = pred[b, :, 5:5 + nc].max(1)
+        sc = pred[b, :, 4] * cc
+        cand = torch.nonzero(sc >= conf)[:, 0]
+        kept_mask = torch.zeros(rows, dtype=torch.bool, device=DEV)
+        kept_mask[kidx] = True
+        dropped = cand[~kept_mask[cand]][:2000]
+        io = bbox.box_iou(pred[b, dropped, :4].contiguous(), det[:, :4].contiguous())
+        cover = (io > iou) & (cp[dropped][:, None].float() == cls[None, :]) & (score[None, :] >= sc[dropped][:, None])
+        assert bool(cover.any(1).all())
+    # idempotence: NMS of its own output keeps everything (scores/classes rebuilt from the kept rows)
+    b = 0
+    det = rows_d[off[b]:off[b + 1]]
+    again = torch.zeros(1, det.shape[0], 5 + nc, device=DEV)
+    wh = det[:, 2:4] - det[:, 0:2]
+    again[0, :, 0:2], again[0, :, 2:4] = det[:, 0:2] + wh / 2, wh
+    again[0, :, 4] = det[:, 4]
+    again[0, torch.arange(det.shape[0]), 5 + det[:, 6].long()] = det[:, 5]
+    _, _, c2, _ = detect.nms_device(again, nc, 0.0, iou + 1e-3)
+    assert int(c2[0]) == det.shape[0]
+
+
+def test_bbox_utils_on_device():
+    from yolo_continuous_b200.utils import bbox
+    fx = load("bbox_kat")
+    boxes = torch.from_numpy(fx["boxes"]).to(DEV)
+    for f in bbox.CvtFlag:
+        assert np.array_equal(bbox.cvt_bbox(boxes, f).cpu().numpy(), fx[f"out_{f.value}"])
+    assert bbox.cvt_bbox(torch.from_numpy(fx["xxyy"]).to(DEV), bbox.CvtFlag.CVT_XXYY_XYXY).tolist() == [[1, 3, 2, 5]]
+    assert bbox.cvt_bbox(torch.from_numpy(fx["xxyy"]).to(DEV), bbox.CvtFlag.CVT_XXYY_XYWH).tolist() == [[1.5, 4, 1, 2]]
+    got = bbox.box_iou(torch.from_numpy(fx["iou_b1"]).to(DEV), torch.from_numpy(fx["iou_b2"]).to(DEV))
+    assert np.array_equal(got.cpu().numpy(), fx["iou"])
+    g = torch.Generator().manual_seed(0)
+    b1 = torch.rand(3, 4, generator=g); b2 = torch.rand(5, 4, generator=g)
+    b1[:, 2:] += b1[:, :2]; b2[:, 2:] += b2[:, :2]
+    assert np.array_equal(bbox.box_iou(b1.to(DEV), b2.to(DEV)).cpu().numpy(), orc.box_iou(b1.numpy(), b2.numpy()))
+
+
+def test_end_to_end_idetect_then_nms_matches_oracle_pipeline():
+    """features -> IDetect -> /input size -> NMS+letterbox undo == the oracle pipeline, modulo
+    candidates whose score lies within tolerance of the confidence threshold."""
+    from yolo_continuous_b200 import detect
+    head, xs = _random_head_case("idetect", 80, (64, 128, 256), [(16, 16), (8, 8), (4, 4)], 2, 21, torch.float32)
+    p = _oracle_params(head, "idetect", False)
+    z_ref, _ = orc.head_forward("idetect", p, [x.numpy() for x in xs], [8.0, 16.0, 32.0])
+    z_ref = z_ref.copy()
+    z_ref[..., :4] /= np.float32(128.0)
+    conf, iou = 0.05, 0.45
+    sc = z_ref[..., 4] * z_ref[..., 5:].max(-1)
+    assert (np.abs(sc - conf) < 1e-5).sum() == 0, "pick another seed: a score sits on the threshold"
+    want, widx = orc.non_max_suppression(z_ref, 80, (128, 128), (96, 128), True, conf, iou, return_indices=True)
+    head = head.to(DEV)
+    got = detect.detect_post_backbone(head, [x.to(DEV) for x in xs], (128, 128), (96, 128), True, conf, iou)
+    for b in range(2):
+        assert (got[b] is None) == (want[b] is None)
+        if want[b] is not None:
+            assert got[b].shape == want[b].shape
+            assert np.array_equal(got[b][:, 6], want[b][:, 6])
+            np.testing.assert_allclose(got[b][:, :6], want[b][:, :6], rtol=2e-4, atol=2e-3)

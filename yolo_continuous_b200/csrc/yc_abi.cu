@@ -1,0 +1,138 @@
+// yc_abi.cu -- C-ABI plumbing: error text, argument validation, dispatch between the tcgen05 head
+// kernel and the any-shape path, and the small box utilities of utils/bbox.py.
+#include <stdarg.h>
+#include <string.h>
+
+#include "yc_common.cuh"
+
+namespace yc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return YC_ERR_CUDA;
+}
+
+int launch_head_generic(const yc_head_desc *d, int rows_total, const int *row_off, cudaStream_t stream);
+// returns YC_ERR_UNSUPPORTED (with the reason in yc_last_error) when the shape does not fit
+int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, cudaStream_t stream);
+
+// utils/bbox.py:62-72
+__global__ void box_iou_kernel(const float4 *__restrict__ b1, int n, const float4 *__restrict__ b2, int m,
+                               float *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * m) return;
+    const float4 a = b1[i / m], b = b2[i % m];
+    const float a1 = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const float a2 = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
+    const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+    const float inter = __fmul_rn(w, h);
+    out[i] = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a1, a2), inter));
+}
+
+// utils/bbox.py:29-59 (tensor branch: the result starts as a clone of the input)
+__global__ void cvt_bbox_kernel(const float4 *__restrict__ in, int n, int flag, float4 *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = in[i];
+    float4 r = b;
+    switch (flag) {
+    case 0: case 2: r.y = b.z; r.z = b.y; break;
+    case 1:
+        r.z = __fsub_rn(b.y, b.x); r.w = __fsub_rn(b.w, b.z);
+        r.x = __fadd_rn(b.x, __fmul_rn(r.z, 0.5f)); r.y = __fadd_rn(b.z, __fmul_rn(r.w, 0.5f)); break;
+    case 3:
+        r.z = __fsub_rn(b.z, b.x); r.w = __fsub_rn(b.w, b.y);
+        r.x = __fadd_rn(b.x, __fmul_rn(r.z, 0.5f)); r.y = __fadd_rn(b.y, __fmul_rn(r.w, 0.5f)); break;
+    case 4:
+        r.x = __fsub_rn(b.x, __fmul_rn(b.z, 0.5f)); r.y = __fadd_rn(b.x, __fmul_rn(b.z, 0.5f));
+        r.z = __fsub_rn(b.y, __fmul_rn(b.w, 0.5f)); r.w = __fadd_rn(b.y, __fmul_rn(b.w, 0.5f)); break;
+    case 5:
+        r.x = __fsub_rn(b.x, __fmul_rn(b.z, 0.5f)); r.y = __fsub_rn(b.y, __fmul_rn(b.w, 0.5f));
+        r.z = __fadd_rn(b.x, __fmul_rn(b.z, 0.5f)); r.w = __fadd_rn(b.y, __fmul_rn(b.w, 0.5f)); break;
+    }
+    out[i] = r;
+}
+
+} // namespace yc
+
+using namespace yc;
+
+extern "C" const char *yc_last_error(void) { return g_err; }
+extern "C" int yc_version(void) { return 100; }
+
+extern "C" int yc_device_check(int dev)
+{
+    cudaDeviceProp prop;
+    YC_CUDA(cudaGetDeviceProperties(&prop, dev));
+    YC_REQUIRE(prop.major == 10, YC_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+               prop.major, prop.minor);
+    return YC_OK;
+}
+
+extern "C" int yc_head_forward(const yc_head_desc *d, yc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    YC_REQUIRE(d, YC_ERR_INVALID, "yc_head_forward: null descriptor");
+    YC_REQUIRE(d->nl >= 1 && d->nl <= YC_MAX_LEVELS && d->na >= 1 && d->na <= YC_MAX_ANCHORS && d->no >= 5 && d->bs >= 1,
+               YC_ERR_INVALID, "yc_head_forward: bad nl=%d na=%d no=%d bs=%d", d->nl, d->na, d->no, d->bs);
+    YC_REQUIRE(d->kind >= YC_HEAD_IDETECT && d->kind <= YC_HEAD_RAW, YC_ERR_INVALID, "yc_head_forward: bad kind %d",
+               d->kind);
+    YC_REQUIRE(d->x_dtype == YC_F32 || d->x_dtype == YC_BF16, YC_ERR_INVALID, "yc_head_forward: bad x_dtype %d",
+               d->x_dtype);
+    YC_REQUIRE(d->kind == YC_HEAD_RAW || d->z, YC_ERR_INVALID, "yc_head_forward: z is null");
+    if (d->kind == YC_HEAD_IBIN) {
+        YC_REQUIRE(d->bins && d->bin_count >= 1 && d->no > 2 * (d->bin_count + 1) + 3, YC_ERR_INVALID,
+                   "yc_head_forward: IBin needs bins and no > 2*(bin_count+1)+3");
+    }
+    int row_off[YC_MAX_LEVELS], rows_total = 0;
+    for (int i = 0; i < d->nl; ++i) {
+        const yc_head_level &lv = d->level[i];
+        YC_REQUIRE(lv.x && lv.blob && lv.K > 0 && lv.H > 0 && lv.W > 0, YC_ERR_INVALID,
+                   "yc_head_forward: level %d has a null pointer or empty shape", i);
+        YC_REQUIRE(d->kind != YC_HEAD_RAW || lv.raw, YC_ERR_INVALID, "yc_head_forward: YC_HEAD_RAW needs raw buffers");
+        row_off[i] = rows_total;
+        rows_total += d->na * lv.H * lv.W;
+    }
+    YC_REQUIRE((size_t)d->bs * rows_total < ((size_t)1 << 31), YC_ERR_UNSUPPORTED, "yc_head_forward: bs*rows >= 2^31");
+    if (d->path == YC_PATH_GENERIC) return launch_head_generic(d, rows_total, row_off, stream);
+    const int rc = launch_head_tcgen05(d, rows_total, row_off, stream);
+    if (rc == YC_ERR_UNSUPPORTED && d->path == YC_PATH_AUTO) return launch_head_generic(d, rows_total, row_off, stream);
+    return rc;
+}
+
+extern "C" int yc_box_iou(const float *b1, int n, const float *b2, int m, float *out, yc_stream_t stream)
+{
+    if (n <= 0 || m <= 0) return YC_OK;
+    YC_REQUIRE(b1 && b2 && out, YC_ERR_INVALID, "yc_box_iou: null argument");
+    YC_REQUIRE((((uintptr_t)b1 | (uintptr_t)b2) & 15) == 0, YC_ERR_INVALID, "yc_box_iou: boxes must be 16-byte aligned");
+    const size_t total = (size_t)n * m;
+    box_iou_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4 *)b1, n,
+                                                                                      (const float4 *)b2, m, out);
+    YC_CUDA(cudaGetLastError());
+    return YC_OK;
+}
+
+extern "C" int yc_cvt_bbox(const float *in, int n, int flag, float *out, yc_stream_t stream)
+{
+    YC_REQUIRE(flag >= 0 && flag <= 5, YC_ERR_INVALID, "yc_cvt_bbox: bad flag %d", flag);
+    if (n <= 0) return YC_OK;
+    YC_REQUIRE(in && out, YC_ERR_INVALID, "yc_cvt_bbox: null argument");
+    YC_REQUIRE((((uintptr_t)in | (uintptr_t)out) & 15) == 0, YC_ERR_INVALID, "yc_cvt_bbox: boxes must be 16-byte aligned");
+    cvt_bbox_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4 *)in, n, flag, (float4 *)out);
+    YC_CUDA(cudaGetLastError());
+    return YC_OK;
+}

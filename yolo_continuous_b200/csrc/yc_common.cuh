@@ -1,0 +1,93 @@
+// yc_common.cuh -- shared helpers for the sm_100a kernels of the detection post-backbone path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/yc_b200.h"
+
+namespace yc {
+
+// ---- error plumbing (thread-local text behind yc_last_error) -----------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define YC_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return yc::cuda_fail(_e, #call);    \
+    } while (0)
+
+#define YC_REQUIRE(cond, code, ...)          \
+    do {                                     \
+        if (!(cond)) {                       \
+            yc::set_error(__VA_ARGS__);      \
+            return (code);                   \
+        }                                    \
+    } while (0)
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline size_t round_up_sz(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- blob layout produced by yc_head_pack (see include/yc_b200.h) ------------------------
+struct BlobView {
+    const float *bias2;       // im * (b + W.ia)
+    const float *scale;       // im
+    const float *scale_split; // im * 2^-shift(c)   (fp16 hi/lo path)
+    const float *w32;         // [N,K]
+    const __half *w_hi;       // [Npad,K]  fp16(W * 2^shift)
+    const __half *w_lo;       // [Npad,K]  fp16(W * 2^shift - w_hi)
+    const __nv_bfloat16 *w_bf; // [Npad,K]
+};
+
+static inline size_t blob_off_scale(int Npad) { return sizeof(float) * (size_t)Npad; }
+
+__host__ __device__ inline BlobView blob_view(const void *blob, int N, int K)
+{
+    const int Npad = (N + 15) / 16 * 16;
+    const char *p = (const char *)blob;
+    BlobView v;
+    v.bias2 = (const float *)p;                  p += sizeof(float) * (size_t)Npad;
+    v.scale = (const float *)p;                  p += sizeof(float) * (size_t)Npad;
+    v.scale_split = (const float *)p;            p += sizeof(float) * (size_t)Npad;
+    size_t w32b = sizeof(float) * (size_t)N * K;
+    w32b = (w32b + 127) / 128 * 128;
+    v.w32 = (const float *)p;                    p += w32b;
+    size_t w16b = sizeof(__half) * (size_t)Npad * K;
+    w16b = (w16b + 127) / 128 * 128;
+    v.w_hi = (const __half *)p;                  p += w16b;
+    v.w_lo = (const __half *)p;                  p += w16b;
+    v.w_bf = (const __nv_bfloat16 *)p;
+    return v;
+}
+
+// ---- numerics shared by every decode epilogue ---------------------------------------------
+// sigmoid in binary32: 1/(1+exp(-t)).  ex2.approx + rcp keep the relative error near 3e-7,
+// inside the 1e-5 parity bound with margin.
+__device__ __forceinline__ float sigmoidf_fast(float t)
+{
+    return __fdividef(1.0f, 1.0f + __expf(-t));
+}
+
+// xy = (s*2 - 0.5 + g) * stride, evaluated in the reference's operation order
+// (nets/idetect.py:41) with no fused multiply-add.
+__device__ __forceinline__ float decode_xy(float s, float g, float stride)
+{
+    float v = __fmul_rn(s, 2.0f);
+    v = __fadd_rn(v, -0.5f);
+    v = __fadd_rn(v, g);
+    return __fmul_rn(v, stride);
+}
+
+// wh = (s*2)**2 * anchor (nets/idetect.py:42)
+__device__ __forceinline__ float decode_wh(float s, float anchor)
+{
+    float v = __fmul_rn(s, 2.0f);
+    v = __fmul_rn(v, v);
+    return __fmul_rn(v, anchor);
+}
+
+} // namespace yc

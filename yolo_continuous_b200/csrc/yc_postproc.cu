@@ -1,0 +1,550 @@
+// yc_postproc.cu -- confidence threshold + stream compaction, class bucketing, per-(image,class)
+// sort + blocked greedy NMS, gather (+ letterbox undo).  Replaces detect.non_max_suppression
+// (reference detect.py:90-144) and torchvision.ops.nms (detect.py:133) for a whole batch with
+// no host round trip.  All comparisons that decide membership are evaluated exactly as the
+// reference evaluates them (binary32, round-to-nearest, no FMA contraction).
+#include "yc_common.cuh"
+
+namespace yc {
+
+constexpr int TC_ROWS = 128;    // rows per CTA in the threshold/compaction kernel
+constexpr int NMS_NT = 128;     // threads per NMS CTA == sorted boxes per chunk
+constexpr int SORT_SMEM = 2048; // segments up to this size are sorted in shared memory
+constexpr int KEPT_SMEM = 512;  // kept boxes cached in shared memory per segment
+
+struct NmsWs {
+    float4 *box;                    // [bs*rows] corners, indexed by original row
+    float2 *oc;                     // [bs*rows] (obj, class_conf)
+    unsigned long long *key_unsorted; // [bs*rows] candidates in arrival order, per image
+    int *cls_unsorted;              // [bs*rows]
+    unsigned long long *key_bucket; // [bs*rows] candidates grouped by class, then sorted in place
+    int *kept_row;                  // [bs*rows] kept original rows, per segment
+    float4 *kept_box;               // [bs*rows] spill of kept boxes beyond KEPT_SMEM
+    int *counters;                  // start of the zero-initialised region
+    int *cand_count;                // [bs]
+    int *hist;                      // [bs*nc] candidates per (image, class)
+    int *cursor;                    // [bs*nc]
+    int *kept_count;                // [bs*nc]
+    int *seg_off;                   // [bs*nc]
+    int *kept_off;                  // [bs*nc]
+    size_t counters_bytes;
+    size_t total_bytes;
+};
+
+static NmsWs carve(void *base, int bs, int rows, int nc)
+{
+    NmsWs w;
+    char *p = (char *)base;
+    const size_t n = (size_t)bs * rows, s = (size_t)bs * nc;
+    auto take = [&](size_t bytes) { char *q = p; p += round_up_sz(bytes, 256); return q; };
+    w.box = (float4 *)take(n * sizeof(float4));
+    w.kept_box = (float4 *)take(n * sizeof(float4));
+    w.key_unsorted = (unsigned long long *)take(n * 8);
+    w.key_bucket = (unsigned long long *)take(n * 8);
+    w.oc = (float2 *)take(n * sizeof(float2));
+    w.cls_unsorted = (int *)take(n * 4);
+    w.kept_row = (int *)take(n * 4);
+    char *c0 = p;
+    w.cand_count = (int *)take((size_t)bs * 4);
+    w.hist = (int *)take(s * 4);
+    w.cursor = (int *)take(s * 4);
+    w.kept_count = (int *)take(s * 4);
+    w.counters = (int *)c0;
+    w.counters_bytes = (size_t)(p - c0);
+    w.seg_off = (int *)take(s * 4);
+    w.kept_off = (int *)take(s * 4);
+    w.total_bytes = (size_t)(p - (char *)base);
+    return w;
+}
+
+// score -> 64-bit key whose ascending order is (score descending, original row ascending),
+// i.e. the order of a stable descending sort (torchvision nms; detect.py:133).
+__device__ __forceinline__ unsigned long long make_key(float score, int row)
+{
+    unsigned int u = __float_as_uint(score);
+    if (score == 0.0f) u = 0u; // -0 == +0 for the reference's sort
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)(~u) << 32) | (unsigned int)row;
+}
+
+// ---- mbarrier / bulk-copy helpers (TMA 1D) -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- K1: corners, class max, threshold, compaction (detect.py:98-116) ------------------------
+// One CTA owns TC_ROWS consecutive rows of one image.  The row tile ([128][row_stride] floats,
+// one contiguous span of pred) is staged in shared memory with a single bulk copy when it is
+// 16-byte aligned, so HBM sees full-line requests; each thread then owns one row
+// (stride-row_stride reads are bank-conflict free for odd row_stride such as 85).
+__global__ void __launch_bounds__(TC_ROWS) threshold_compact_kernel(float *__restrict__ pred, int rows, int row_stride,
+                                                                    int nc, float conf, int write_corners, NmsWs ws)
+{
+    extern __shared__ __align__(128) float tile[];
+    __shared__ __align__(8) uint64_t bar;
+    const int b = blockIdx.y, r0 = blockIdx.x * TC_ROWS, tid = threadIdx.x;
+    const int m = min(TC_ROWS, rows - r0);
+    float *src = pred + ((size_t)b * rows + r0) * row_stride;
+    const uint32_t bytes = (uint32_t)m * row_stride * 4u;
+    const bool bulk = (((uintptr_t)src | bytes) & 15u) == 0;
+    if (bulk) {
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, bytes);
+            bulk_g2s(tile, src, bytes, &bar);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        for (int i = tid; i < m * row_stride; i += TC_ROWS) tile[i] = src[i];
+        __syncthreads();
+    }
+    const int r = r0 + tid;
+    bool pass = false;
+    int best = 0;
+    float x1 = 0, y1 = 0, x2 = 0, y2 = 0, obj = 0, bv = 0, score = 0;
+    if (tid < m) {
+        const float *q = tile + tid * row_stride;
+        const float cx = q[0], cy = q[1], hw = __fmul_rn(q[2], 0.5f), hh = __fmul_rn(q[3], 0.5f);
+        x1 = __fsub_rn(cx, hw); y1 = __fsub_rn(cy, hh);
+        x2 = __fadd_rn(cx, hw); y2 = __fadd_rn(cy, hh);
+        obj = q[4];
+        bv = q[5];
+#pragma unroll 8
+        for (int c = 1; c < nc; ++c) {
+            const float v = q[5 + c];
+            if (v > bv) { bv = v; best = c; } // first maximum, as torch.max
+        }
+        score = __fmul_rn(obj, bv);
+        pass = score >= conf;
+        if (write_corners) {
+            float *o = src + (size_t)tid * row_stride;
+            o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+    if (ballot) {
+        const int lane = tid & 31, leader = __ffs(ballot) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&ws.cand_count[b], __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pass) {
+            const size_t ib = (size_t)b * rows;
+            const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+            ws.box[ib + r] = make_float4(x1, y1, x2, y2);
+            ws.oc[ib + r] = make_float2(obj, bv);
+            ws.key_unsorted[ib + slot] = make_key(score, r);
+            ws.cls_unsorted[ib + slot] = best;
+            atomicAdd(&ws.hist[(size_t)b * nc + best], 1);
+        }
+    }
+}
+
+// ---- K2: per-image exclusive scan of the class histogram ----------------------------------------
+__global__ void __launch_bounds__(256) segment_offsets_kernel(int nc, NmsWs ws)
+{
+    __shared__ int warp_tot[8];
+    __shared__ int carry_s;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < nc; c0 += 256) {
+        const int c = c0 + tid;
+        const int v = c < nc ? ws.hist[(size_t)b * nc + c] : 0;
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        int pre = carry_s;
+        for (int w = 0; w < wid; ++w) pre += warp_tot[w];
+        if (c < nc) ws.seg_off[(size_t)b * nc + c] = pre + inc - v;
+        __syncthreads();
+        if (tid == 255) carry_s = pre + inc;
+        __syncthreads();
+    }
+}
+
+// ---- K3: move candidate keys into their class bucket ------------------------------------------------
+__global__ void __launch_bounds__(256) bucket_scatter_kernel(int rows, int nc, NmsWs ws)
+{
+    const int b = blockIdx.y, slot = blockIdx.x * 256 + threadIdx.x;
+    if (slot >= ws.cand_count[b]) return;
+    const size_t ib = (size_t)b * rows;
+    const int cls = ws.cls_unsorted[ib + slot];
+    const int pos = ws.seg_off[(size_t)b * nc + cls] + atomicAdd(&ws.cursor[(size_t)b * nc + cls], 1);
+    ws.key_bucket[ib + pos] = ws.key_unsorted[ib + slot];
+}
+
+// IoU test of torchvision's CPU nms kernel (third-party; call site detect.py:133):
+// inter / (area_a + area_b - inter) > thr, binary32 round-to-nearest throughout, the quotient
+// compared against thr_f = largest binary32 <= the binary64 threshold (equivalent to the
+// reference's promotion of the quotient to binary64).  NaN compares false.
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, const float thr_f)
+{
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    const float aa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const float ab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    const float uni = __fsub_rn(__fadd_rn(aa, ab), inter);
+    return __fdiv_rn(inter, uni) > thr_f;
+}
+
+// ---- K4: one CTA per (image, class) segment: sort, then blocked greedy suppression -----------------
+// Sort: bitonic network with every comparator ascending, so partners beyond n can simply be
+// skipped (equivalent to +inf padding) -- works for any n, in shared memory up to SORT_SMEM keys
+// and in place in global memory above that.
+// Greedy: sorted boxes are consumed in chunks of NMS_NT.  A chunk is first tested against every box
+// kept so far (one thread per box), then a NMS_NT x NMS_NT upper-triangular IoU bitmask is built in
+// shared memory and warp 0 walks it: the lane owning the current 64-bit word finds the next
+// surviving box with ffs, all lanes OR that box's mask row into their word.  This is exactly the
+// sequential rule "keep i; suppress every later j with IoU(i,j) > thr" of the reference.
+__global__ void __launch_bounds__(NMS_NT) nms_segment_kernel(int rows, int nc, float thr_f, NmsWs ws)
+{
+    __shared__ unsigned long long skeys[SORT_SMEM];
+    __shared__ float4 sbox[NMS_NT];
+    __shared__ float4 skept[KEPT_SMEM];
+    __shared__ unsigned long long smask[NMS_NT][2];
+    __shared__ unsigned int sdead[NMS_NT / 32];
+    __shared__ int s_nkept;
+
+    const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t seg = (size_t)b * nc + c;
+    const int n = ws.hist[seg];
+    if (n == 0) return; // kept_count stays 0
+    const size_t ib = (size_t)b * rows;
+    const int off = ws.seg_off[seg];
+    unsigned long long *gkeys = ws.key_bucket + ib + off;
+    int *kept_row = ws.kept_row + ib + off;
+    float4 *kept_box = ws.kept_box + ib + off;
+
+    if (n == 1) {
+        if (tid == 0) {
+            kept_row[0] = (int)(gkeys[0] & 0xffffffffull);
+            ws.kept_count[seg] = 1;
+        }
+        return;
+    }
+
+    unsigned long long *K = gkeys;
+    if (n <= SORT_SMEM) {
+        for (int i = tid; i < n; i += NMS_NT) skeys[i] = gkeys[i];
+        K = skeys;
+    }
+    __syncthreads();
+    for (int k = 2; (k >> 1) < n; k <<= 1) {
+        for (int i = tid; i < n; i += NMS_NT) {
+            const int l = i ^ (k - 1);
+            if (l > i && l < n) {
+                const unsigned long long a = K[i], d = K[l];
+                if (a > d) { K[i] = d; K[l] = a; }
+            }
+        }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = tid; i < n; i += NMS_NT) {
+                const int l = i ^ j;
+                if (l > i && l < n) {
+                    const unsigned long long a = K[i], d = K[l];
+                    if (a > d) { K[i] = d; K[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    if (tid == 0) s_nkept = 0;
+    __syncthreads();
+
+    for (int base = 0; base < n; base += NMS_NT) {
+        const int m = min(NMS_NT, n - base);
+        float4 bx = make_float4(0, 0, 0, 0);
+        if (tid < m) {
+            const int row = (int)(K[base + tid] & 0xffffffffull);
+            bx = ws.box[ib + row];
+            sbox[tid] = bx;
+        }
+        const int nk = s_nkept;
+        __syncthreads();
+        bool dead = tid >= m;
+        if (!dead) {
+            for (int k = 0; k < nk; ++k) {
+                const float4 kb = k < KEPT_SMEM ? skept[k] : kept_box[k];
+                if (iou_gt(kb, bx, thr_f)) { dead = true; break; }
+            }
+        }
+        unsigned long long m0 = 0, m1 = 0;
+        if (!dead) {
+            for (int j = tid + 1; j < m; ++j) {
+                if (iou_gt(bx, sbox[j], thr_f)) {
+                    if (j < 64) m0 |= 1ull << j;
+                    else m1 |= 1ull << (j - 64);
+                }
+            }
+        }
+        smask[tid][0] = m0;
+        smask[tid][1] = m1;
+        const unsigned d = __ballot_sync(0xffffffffu, dead);
+        if (lane == 0) sdead[wid] = d;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long remv = 0;
+            if (lane < 2) remv = (unsigned long long)sdead[2 * lane] | ((unsigned long long)sdead[2 * lane + 1] << 32);
+            int cnt = nk;
+            for (int w = 0; w < 2; ++w) {
+                while (true) {
+                    const unsigned long long cur = __shfl_sync(0xffffffffu, remv, w);
+                    const unsigned long long alive = ~cur;
+                    if (!alive) break;
+                    const int i = __ffsll((long long)alive) - 1;
+                    const int idx = w * 64 + i;
+                    if (lane < 2) remv |= smask[idx][lane];
+                    if (lane == w) remv |= 1ull << i;
+                    if (lane == 0) {
+                        const float4 kb = sbox[idx];
+                        kept_row[cnt] = (int)(K[base + idx] & 0xffffffffull);
+                        if (cnt < KEPT_SMEM) skept[cnt] = kb;
+                        else kept_box[cnt] = kb;
+                    }
+                    ++cnt;
+                }
+            }
+            if (lane == 0) s_nkept = cnt;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) ws.kept_count[seg] = s_nkept;
+}
+
+// ---- K5: output offsets: per-image scan over classes, then scan over images --------------------
+__global__ void __launch_bounds__(1024) kept_scan_kernel(int bs, int nc, NmsWs ws, int *out_counts, int *out_offsets)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int b = wid; b < bs; b += 32) {
+        int running = 0;
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+            const int c = c0 + lane;
+            const int v = c < nc ? ws.kept_count[(size_t)b * nc + c] : 0;
+            int inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (c < nc) ws.kept_off[(size_t)b * nc + c] = running + inc - v;
+            running += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) out_counts[b] = running;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        int running = 0;
+        for (int b0 = 0; b0 < bs; b0 += 32) {
+            const int b = b0 + lane;
+            const int v = b < bs ? out_counts[b] : 0;
+            int inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (b < bs) out_offsets[b] = running + inc - v;
+            running += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) out_offsets[bs] = running;
+    }
+}
+
+// ---- K6: assemble output rows (detect.py:121,137) and optionally undo the letterbox ---------------
+// yolo_correct_boxes (detect.py:140-142,147-165) is evaluated with numpy's promotion rules:
+// binary64 when letterbox_image is set (except box_hw *= scale, rounded back to binary32),
+// binary32 until the final multiply by the image shape otherwise; the result is stored as binary32.
+struct CorrectParams {
+    int enabled, letterbox, in_h, in_w;
+    const int *image_hw;
+    int image_hw_stride;
+};
+
+__global__ void __launch_bounds__(128) gather_kernel(int rows, int nc, NmsWs ws, const int *__restrict__ out_offsets,
+                                                     float *__restrict__ out_rows, int *__restrict__ out_idx,
+                                                     CorrectParams cp)
+{
+    const int b = blockIdx.y, c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= nc) return;
+    const size_t seg = (size_t)b * nc + c;
+    const int nk = ws.kept_count[seg];
+    if (nk == 0) return;
+    const size_t ib = (size_t)b * rows;
+    const int *kept_row = ws.kept_row + ib + ws.seg_off[seg];
+    const size_t obase = (size_t)out_offsets[b] + ws.kept_off[seg];
+    double off[2] = {0, 0}, scl[2] = {1, 1}, ims[2] = {1, 1};
+    if (cp.enabled) {
+        const int *hw = cp.image_hw + (size_t)b * cp.image_hw_stride;
+        ims[0] = (double)hw[0]; ims[1] = (double)hw[1];
+        if (cp.letterbox) {
+            const double ins[2] = {(double)cp.in_h, (double)cp.in_w};
+            const double r = fmin(ins[0] / ims[0], ins[1] / ims[1]);
+            for (int d = 0; d < 2; ++d) {
+                const double ns = rint(ims[d] * r);
+                off[d] = (ins[d] - ns) / 2.0 / ins[d];
+                scl[d] = ins[d] / ns;
+            }
+        }
+    }
+    for (int k = lane; k < nk; k += 32) {
+        const int row = kept_row[k];
+        const float4 bx = ws.box[ib + row];
+        const float2 oc = ws.oc[ib + row];
+        float o0 = bx.x, o1 = bx.y, o2 = bx.z, o3 = bx.w;
+        if (cp.enabled) {
+            const float yx[2] = {__fmul_rn(__fadd_rn(bx.y, bx.w), 0.5f), __fmul_rn(__fadd_rn(bx.x, bx.z), 0.5f)};
+            const float hw[2] = {__fsub_rn(bx.w, bx.y), __fsub_rn(bx.z, bx.x)};
+            float mn[2], mx[2];
+            if (cp.letterbox) {
+                for (int d = 0; d < 2; ++d) {
+                    const double v = __dmul_rn(__dsub_rn((double)yx[d], off[d]), scl[d]);
+                    const float h32 = (float)__dmul_rn((double)hw[d], scl[d]);
+                    const double half = (double)__fmul_rn(h32, 0.5f);
+                    mn[d] = (float)__dmul_rn(__dsub_rn(v, half), ims[d]);
+                    mx[d] = (float)__dmul_rn(__dadd_rn(v, half), ims[d]);
+                }
+            } else {
+                for (int d = 0; d < 2; ++d) {
+                    const float half = __fmul_rn(hw[d], 0.5f);
+                    mn[d] = (float)__dmul_rn((double)__fsub_rn(yx[d], half), ims[d]);
+                    mx[d] = (float)__dmul_rn((double)__fadd_rn(yx[d], half), ims[d]);
+                }
+            }
+            o0 = mn[0]; o1 = mn[1]; o2 = mx[0]; o3 = mx[1];
+        }
+        float *o = out_rows + (obase + k) * 7;
+        o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+        o[4] = oc.x; o[5] = oc.y; o[6] = (float)c;
+        out_idx[obase + k] = row;
+    }
+}
+
+// ---- torchvision.ops.nms drop-in for one box set ---------------------------------------------------
+__global__ void single_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, int n, NmsWs ws)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { ws.hist[0] = n; ws.seg_off[0] = 0; }
+    if (i >= n) return;
+    ws.box[i] = make_float4(boxes[4 * i], boxes[4 * i + 1], boxes[4 * i + 2], boxes[4 * i + 3]);
+    ws.key_bucket[i] = make_key(scores[i], i);
+}
+
+__global__ void single_finish_kernel(NmsWs ws, int *keep, int *keep_count)
+{
+    const int nk = ws.kept_count[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nk; i += gridDim.x * blockDim.x) keep[i] = ws.kept_row[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *keep_count = nk;
+}
+
+static float thr_to_f32_floor(double thr)
+{
+    float tf = (float)thr;
+    if ((double)tf > thr) tf = nextafterf(tf, -INFINITY);
+    return tf;
+}
+
+} // namespace yc
+
+using namespace yc;
+
+extern "C" size_t yc_nms_workspace_bytes(int bs, int rows, int nc)
+{
+    if (bs <= 0 || rows <= 0 || nc <= 0) return 0;
+    return carve(nullptr, bs, rows, nc).total_bytes + 256;
+}
+
+extern "C" int yc_nms_batched(float *pred, const yc_nms_params *p, void *workspace, size_t workspace_bytes,
+                              float *out_rows, int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets,
+                              yc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    YC_REQUIRE(p && pred && workspace && out_rows && out_idx && out_counts && out_offsets, YC_ERR_INVALID,
+               "yc_nms_batched: null argument");
+    YC_REQUIRE(p->bs > 0 && p->rows > 0 && p->nc > 0 && p->row_stride >= 5 + p->nc, YC_ERR_INVALID,
+               "yc_nms_batched: bad shape bs=%d rows=%d nc=%d row_stride=%d", p->bs, p->rows, p->nc, p->row_stride);
+    YC_REQUIRE((size_t)p->bs * p->rows < (size_t)1 << 31, YC_ERR_UNSUPPORTED, "yc_nms_batched: bs*rows >= 2^31");
+    YC_REQUIRE(p->bs <= 65535, YC_ERR_UNSUPPORTED, "yc_nms_batched: bs > 65535");
+    YC_REQUIRE(!p->correct_boxes || p->image_hw, YC_ERR_INVALID, "yc_nms_batched: correct_boxes needs image_hw");
+    void *base = (void *)round_up_sz((size_t)workspace, 256);
+    NmsWs ws = carve(base, p->bs, p->rows, p->nc);
+    YC_REQUIRE(ws.total_bytes + ((char *)base - (char *)workspace) <= workspace_bytes, YC_ERR_WORKSPACE,
+               "yc_nms_batched: workspace %zu < %zu", workspace_bytes, ws.total_bytes + 256);
+    const size_t tile_bytes = (size_t)TC_ROWS * p->row_stride * 4;
+    YC_REQUIRE(tile_bytes <= 200 * 1024, YC_ERR_UNSUPPORTED, "yc_nms_batched: row_stride %d too large", p->row_stride);
+
+    YC_CUDA(cudaMemsetAsync(ws.counters, 0, ws.counters_bytes, stream));
+    if (tile_bytes > 48 * 1024)
+        YC_CUDA(cudaFuncSetAttribute(threshold_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tile_bytes));
+    dim3 g1((p->rows + TC_ROWS - 1) / TC_ROWS, p->bs);
+    threshold_compact_kernel<<<g1, TC_ROWS, tile_bytes, stream>>>(pred, p->rows, p->row_stride, p->nc, p->conf_thres,
+                                                                  p->write_corners, ws);
+    segment_offsets_kernel<<<p->bs, 256, 0, stream>>>(p->nc, ws);
+    bucket_scatter_kernel<<<dim3((p->rows + 255) / 256, p->bs), 256, 0, stream>>>(p->rows, p->nc, ws);
+    nms_segment_kernel<<<dim3(p->nc, p->bs), NMS_NT, 0, stream>>>(p->rows, p->nc, thr_to_f32_floor(p->nms_thres), ws);
+    kept_scan_kernel<<<1, 1024, 0, stream>>>(p->bs, p->nc, ws, out_counts, out_offsets);
+    CorrectParams cp{p->correct_boxes, p->letterbox, p->input_h, p->input_w, p->image_hw, p->image_hw_stride};
+    gather_kernel<<<dim3((p->nc + 3) / 4, p->bs), 128, 0, stream>>>(p->rows, p->nc, ws, out_offsets, out_rows, out_idx,
+                                                                    cp);
+    YC_CUDA(cudaGetLastError());
+    return YC_OK;
+}
+
+extern "C" int yc_nms_single(const float *boxes, const float *scores, int n, double thr, void *workspace,
+                             size_t workspace_bytes, int32_t *keep, int32_t *keep_count_dev, yc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    YC_REQUIRE(keep_count_dev && workspace, YC_ERR_INVALID, "yc_nms_single: null argument");
+    if (n <= 0) {
+        YC_CUDA(cudaMemsetAsync(keep_count_dev, 0, sizeof(int), stream));
+        return YC_OK;
+    }
+    YC_REQUIRE(boxes && scores && keep, YC_ERR_INVALID, "yc_nms_single: null argument");
+    void *base = (void *)round_up_sz((size_t)workspace, 256);
+    NmsWs ws = carve(base, 1, n, 1);
+    YC_REQUIRE(ws.total_bytes + ((char *)base - (char *)workspace) <= workspace_bytes, YC_ERR_WORKSPACE,
+               "yc_nms_single: workspace %zu < %zu", workspace_bytes, ws.total_bytes + 256);
+    YC_CUDA(cudaMemsetAsync(ws.counters, 0, ws.counters_bytes, stream));
+    single_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(boxes, scores, n, ws);
+    nms_segment_kernel<<<dim3(1, 1), NMS_NT, 0, stream>>>(n, 1, thr_to_f32_floor(thr), ws);
+    single_finish_kernel<<<min((n + 255) / 256, 64), 256, 0, stream>>>(ws, keep, keep_count_dev);
+    YC_CUDA(cudaGetLastError());
+    return YC_OK;
+}

@@ -1,0 +1,161 @@
+// yc_sm100.cuh -- thin inline-PTX wrappers for the Blackwell (sm_100a) features the head kernel
+// uses: mbarrier, TMA (cp.async.bulk[.tensor]), tcgen05 MMA / commit / TMEM alloc / TMEM load.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace yc {
+namespace sm100 {
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// ---- mbarrier --------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// ---- TMA -------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_addr(dst)),
+        "l"(m), "r"(smem_addr(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+        "[%2];" ::"r"(smem_addr(dst)),
+        "l"(m), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// 1-D bulk store shared -> global (16-byte aligned, size multiple of 16)
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy smem writes visible to the async proxy (TMA store reads smem)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- tcgen05 ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16/fp16 inputs, fp32 accumulate)
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when they complete
+__device__ __forceinline__ void mma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
+                 : "memory");
+}
+
+// TMEM -> registers: this warp's 32 lanes x W consecutive 32-bit columns
+template <int W> struct TmemLd;
+#define YC_TMEM_LD_BODY(W_, REGS, OUTS)                                                                       \
+    template <> struct TmemLd<W_> {                                                                           \
+        static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)                                \
+        {                                                                                                     \
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x" #W_ ".b32 {" REGS "}, [%" #W_ "];" : OUTS : "r"(taddr) : "memory"); \
+        }                                                                                                     \
+    };
+YC_TMEM_LD_BODY(1, "%0", "=r"(r[0]))
+YC_TMEM_LD_BODY(2, "%0, %1", "=r"(r[0]), "=r"(r[1]))
+YC_TMEM_LD_BODY(4, "%0, %1, %2, %3", "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]))
+YC_TMEM_LD_BODY(8, "%0, %1, %2, %3, %4, %5, %6, %7",
+                "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]))
+YC_TMEM_LD_BODY(16, "%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15",
+                "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]))
+#undef YC_TMEM_LD_BODY
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors (cute/arch/mma_sm100_desc.hpp layouts, rebuilt from the bit fields) -----------
+// shared-memory matrix descriptor: start[0,14) lbo[16,30) sbo[32,46) version=1 @46 layout_type[61,64)
+enum : uint64_t { SWZ_NONE = 0, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6 };
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout << 61);
+}
+// instruction descriptor, kind::f16: D=f32, A/B format (0=f16, 1=bf16), majors (0=K, 1=MN), N>>3, M>>4
+__host__ __device__ inline uint32_t instr_desc_f16(uint32_t ab_format, uint32_t a_major, uint32_t b_major, uint32_t M,
+                                                   uint32_t N)
+{
+    return (1u << 4) | (ab_format << 7) | (ab_format << 10) | (a_major << 15) | (b_major << 16) | ((N >> 3) << 17) |
+           ((M >> 4) << 24);
+}
+
+} // namespace sm100
+} // namespace yc
