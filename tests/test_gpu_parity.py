@@ -324,3 +324,75 @@ def test_end_to_end_idetect_then_nms_matches_oracle_pipeline():
             assert got[b].shape == want[b].shape
             assert np.array_equal(got[b][:, 6], want[b][:, 6])
             np.testing.assert_allclose(got[b][:, :6], want[b][:, :6], rtol=2e-4, atol=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# tcgen05 / TMEM / TMA head kernel (bf16 feature maps)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["idetect", "iaux"])
+def test_tcgen05_head_vs_oracle_bf16(kind):
+    """Forced tcgen05 path on TMA-compatible ragged shapes (H*W = 240, 72, 24: partial 128-pixel tiles,
+    a second TMA box that is partly / fully out of bounds) against the oracle fed the same
+    bf16-representable inputs."""
+    from yolo_continuous_b200 import _lib
+    mult = 2 if kind == "iaux" else 1
+    ch = (256, 512, 1024) * mult
+    shapes = [(12, 20), (6, 12), (4, 6)] * mult
+    head, xs = _random_head_case(kind, 80, ch, shapes, 3, 9, torch.bfloat16)
+    p = _oracle_params(head, kind, True)
+    res = orc.head_forward(kind, p, [x.float().numpy() for x in xs], [8.0, 16.0, 32.0])
+    head = head.to(DEV)
+    head.head_path = _lib.YC_PATH_TCGEN05
+    lst = [x.to(DEV) for x in xs]
+    z, raws = head(lst)
+    scale = box_scale(p["anchors"], [8.0, 16.0, 32.0], shapes[:3], head.na, z.shape[-1])
+    assert_close_scaled(z.cpu().numpy(), res[0], scale, RTOL_BF16, f"tcgen05/{kind}")
+    # bf16 products are exact in fp32, so what is left is the tensor core's accumulation (not IEEE
+    # round-to-nearest; measured worst case 2.5e-5 at K=1024): far inside the 1e-3 bound
+    assert_close_scaled(z.cpu().numpy(), res[0], scale, 1e-4, f"tcgen05/{kind} (tight)")
+    for i in range(head.nl):
+        np.testing.assert_allclose(raws[i].cpu().numpy(), res[1][i], rtol=0, atol=1e-4)
+    if kind == "iaux":
+        for i in range(head.nl):
+            np.testing.assert_allclose(lst[i + head.nl].cpu().numpy(), res[2][i], rtol=0, atol=1e-4)
+    # z only (no raw maps) and train mode (raw maps only) go through different epilogue branches
+    head.return_raw = False
+    z2, _ = head([x.to(DEV) for x in xs])
+    assert torch.equal(z2, z)
+    head.return_raw = True
+    head.train()
+    tr = head([x.to(DEV) for x in xs])
+    for i in range(head.nl):
+        assert torch.equal(tr[i], raws[i])
+
+
+def test_tcgen05_head_tiny_nc1():
+    """nc=1 (config C1 shape: N = 18 -> one 32-column MMA), even row length (6 floats)."""
+    from yolo_continuous_b200 import _lib
+    head, xs = _random_head_case("idetect", 1, (128, 256, 512), [(8, 16), (4, 8), (2, 4)], 2, 5, torch.bfloat16)
+    p = _oracle_params(head, "idetect", True)
+    z_ref, raw_ref = orc.head_forward("idetect", p, [x.float().numpy() for x in xs], [8.0, 16.0, 32.0])
+    head = head.to(DEV)
+    head.head_path = _lib.YC_PATH_TCGEN05
+    z, raws = head([x.to(DEV) for x in xs])
+    scale = box_scale(p["anchors"], [8.0, 16.0, 32.0], [(8, 16), (4, 8), (2, 4)], 3, 6)
+    assert_close_scaled(z.cpu().numpy(), z_ref, scale, 1e-4, "tcgen05/nc1")
+
+
+def test_tcgen05_head_full_size_vs_generic_kernel():
+    """COCO head at 640x640 (25 200 rows/img), bs=4: tcgen05 kernel against the exact-FFMA kernel on the
+    same bf16 inputs (both accumulate bf16 products in fp32; only the summation order differs)."""
+    from yolo_continuous_b200 import _lib
+    head, _ = _random_head_case("idetect", 80, (256, 512, 1024), [(1, 8)] * 3, 1, 13, torch.bfloat16)
+    head = head.to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1234)
+    xs = [torch.randn(4, c, s, s, generator=g, device=DEV).to(torch.bfloat16) for c, s in zip((256, 512, 1024), (80, 40, 20))]
+    head.head_path = _lib.YC_PATH_GENERIC
+    z_g, raw_g = head(list(xs))
+    head.head_path = _lib.YC_PATH_TCGEN05
+    z_t, raw_t = head(list(xs))
+    assert z_t.shape == (4, 25200, 85)
+    for a_, b_ in zip(raw_t, raw_g):
+        assert float((a_ - b_).abs().max()) < 1e-4
+    rel = (z_t - z_g).abs() / z_g.abs().clamp_min(8.0)
+    assert float(rel.max()) < 1e-4

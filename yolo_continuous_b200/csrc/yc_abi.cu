@@ -23,9 +23,12 @@ int cuda_fail(cudaError_t e, const char *what)
     return YC_ERR_CUDA;
 }
 
-int launch_head_generic(const yc_head_desc *d, int rows_total, const int *row_off, cudaStream_t stream);
-// returns YC_ERR_UNSUPPORTED (with the reason in yc_last_error) when the shape does not fit
-int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, cudaStream_t stream);
+int launch_head_generic(const yc_head_desc *d, int rows_total, const int *row_off, unsigned level_mask,
+                        cudaStream_t stream);
+// Runs the levels that fit the tcgen05 kernel and reports the others in *left_mask; returns
+// YC_ERR_UNSUPPORTED (reason in yc_last_error) when the head as a whole does not fit.
+int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, unsigned *left_mask,
+                        cudaStream_t stream);
 
 // utils/bbox.py:62-72
 __global__ void box_iou_kernel(const float4 *__restrict__ b1, int n, const float4 *__restrict__ b2, int m,
@@ -108,10 +111,18 @@ extern "C" int yc_head_forward(const yc_head_desc *d, yc_stream_t stream_)
         rows_total += d->na * lv.H * lv.W;
     }
     YC_REQUIRE((size_t)d->bs * rows_total < ((size_t)1 << 31), YC_ERR_UNSUPPORTED, "yc_head_forward: bs*rows >= 2^31");
-    if (d->path == YC_PATH_GENERIC) return launch_head_generic(d, rows_total, row_off, stream);
-    const int rc = launch_head_tcgen05(d, rows_total, row_off, stream);
-    if (rc == YC_ERR_UNSUPPORTED && d->path == YC_PATH_AUTO) return launch_head_generic(d, rows_total, row_off, stream);
-    return rc;
+    const unsigned all = (1u << d->nl) - 1u;
+    if (d->path == YC_PATH_GENERIC) return launch_head_generic(d, rows_total, row_off, all, stream);
+    unsigned left = all;
+    const int rc = launch_head_tcgen05(d, rows_total, row_off, &left, stream);
+    if (rc == YC_ERR_UNSUPPORTED && d->path == YC_PATH_AUTO) return launch_head_generic(d, rows_total, row_off, all, stream);
+    if (rc != YC_OK) return rc;
+    if (left) {
+        YC_REQUIRE(d->path == YC_PATH_AUTO, YC_ERR_UNSUPPORTED, "yc_head_forward: levels 0x%x do not fit the tcgen05 kernel: %s",
+                   left, g_err);
+        return launch_head_generic(d, rows_total, row_off, left, stream);
+    }
+    return YC_OK;
 }
 
 extern "C" int yc_box_iou(const float *b1, int n, const float *b2, int m, float *out, yc_stream_t stream)

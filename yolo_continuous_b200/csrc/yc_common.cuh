@@ -37,6 +37,8 @@ struct BlobView {
     const float *bias2;       // im * (b + W.ia)
     const float *scale;       // im
     const float *scale_split; // im * 2^-shift(c)   (fp16 hi/lo path)
+    const float2 *sb;         // (scale, bias2) interleaved: one 8-byte broadcast load per column in the epilogue
+    const float2 *sb_split;   // (scale_split, bias2)
     const float *w32;         // [N,K]
     const __half *w_hi;       // [Npad,K]  fp16(W * 2^shift)
     const __half *w_lo;       // [Npad,K]  fp16(W * 2^shift - w_hi)
@@ -53,6 +55,8 @@ __host__ __device__ inline BlobView blob_view(const void *blob, int N, int K)
     v.bias2 = (const float *)p;                  p += sizeof(float) * (size_t)Npad;
     v.scale = (const float *)p;                  p += sizeof(float) * (size_t)Npad;
     v.scale_split = (const float *)p;            p += sizeof(float) * (size_t)Npad;
+    v.sb = (const float2 *)p;                    p += sizeof(float2) * (size_t)Npad;
+    v.sb_split = (const float2 *)p;              p += sizeof(float2) * (size_t)Npad;
     size_t w32b = sizeof(float) * (size_t)N * K;
     w32b = (w32b + 127) / 128 * 128;
     v.w32 = (const float *)p;                    p += w32b;

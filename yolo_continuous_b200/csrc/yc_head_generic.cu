@@ -16,7 +16,7 @@ namespace yc {
 __global__ void __launch_bounds__(128) head_pack_kernel(const float *__restrict__ W, const float *__restrict__ bias,
                                                         const float *__restrict__ ia, const float *__restrict__ im, int N,
                                                         int K, int Npad, float *bias2, float *scale, float *scale_split,
-                                                        float *w32, __half *w_hi, __half *w_lo, __nv_bfloat16 *w_bf)
+                                                        float2 *sb, float2 *sb_split, float *w32, __half *w_hi, __half *w_lo, __nv_bfloat16 *w_bf)
 {
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= Npad) return;
@@ -26,7 +26,10 @@ __global__ void __launch_bounds__(128) head_pack_kernel(const float *__restrict_
             w_lo[(size_t)c * K + k] = __float2half_rn(0.f);
             w_bf[(size_t)c * K + k] = __float2bfloat16_rn(0.f);
         }
-        if (lane == 0) { bias2[c] = 0.f; scale[c] = 0.f; scale_split[c] = 0.f; }
+        if (lane == 0) {
+            bias2[c] = 0.f; scale[c] = 0.f; scale_split[c] = 0.f;
+            sb[c] = make_float2(0.f, 0.f); sb_split[c] = make_float2(0.f, 0.f);
+        }
         return;
     }
     const float *wr = W + (size_t)c * K;
@@ -64,6 +67,8 @@ __global__ void __launch_bounds__(128) head_pack_kernel(const float *__restrict_
         bias2[c] = __fmul_rn(m, b1);
         scale[c] = m;
         scale_split[c] = ldexpf(m, -shift);
+        sb[c] = make_float2(m, __fmul_rn(m, b1));
+        sb_split[c] = make_float2(ldexpf(m, -shift), __fmul_rn(m, b1));
     }
 }
 
@@ -228,10 +233,12 @@ __global__ void __launch_bounds__(256) decode_box_kernel(const float *__restrict
 }
 
 // host launcher used by yc_head_forward (yc_abi.cu)
-int launch_head_generic(const yc_head_desc *d, int rows_total, const int *row_off, cudaStream_t stream)
+int launch_head_generic(const yc_head_desc *d, int rows_total, const int *row_off, unsigned level_mask,
+                        cudaStream_t stream)
 {
     const int N = d->na * d->no;
     for (int i = 0; i < d->nl; ++i) {
+        if (!(level_mask >> i & 1u)) continue;
         const yc_head_level &lv = d->level[i];
         const int HW = lv.H * lv.W;
         BlobView bv = blob_view(lv.blob, N, lv.K);
@@ -277,7 +284,7 @@ extern "C" size_t yc_head_pack_bytes(int N, int K)
     const int Npad = round_up(N, 16);
     size_t w32b = round_up_sz(sizeof(float) * (size_t)N * K, 128);
     size_t w16b = round_up_sz(sizeof(__half) * (size_t)Npad * K, 128);
-    return sizeof(float) * 3 * (size_t)Npad + w32b + 3 * w16b + 256;
+    return sizeof(float) * 7 * (size_t)Npad + w32b + 3 * w16b + 256;
 }
 
 extern "C" int yc_head_pack(const float *W, const float *bias, const float *ia, const float *im, int N, int K, void *blob,
@@ -288,7 +295,8 @@ extern "C" int yc_head_pack(const float *W, const float *bias, const float *ia, 
     const int Npad = round_up(N, 16);
     BlobView v = blob_view(blob, N, K);
     head_pack_kernel<<<(Npad + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
-        W, bias, ia, im, N, K, Npad, (float *)v.bias2, (float *)v.scale, (float *)v.scale_split, (float *)v.w32,
+        W, bias, ia, im, N, K, Npad, (float *)v.bias2, (float *)v.scale, (float *)v.scale_split, (float2 *)v.sb, (float2 *)v.sb_split,
+        (float *)v.w32,
         (__half *)v.w_hi, (__half *)v.w_lo, (__nv_bfloat16 *)v.w_bf);
     YC_CUDA(cudaGetLastError());
     return YC_OK;

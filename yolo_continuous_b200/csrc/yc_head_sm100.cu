@@ -1,9 +1,404 @@
-// placeholder, replaced below
+// yc_head_sm100.cu -- the head's 1x1 output convolution as a persistent, warp-specialised
+// tcgen05 / TMEM / TMA kernel for sm_100a, with ImplicitM scale + bias, sigmoid and the grid/anchor
+// box decode fused into the epilogue (reference nets/idetect.py:31-45 in one pass).
+//
+// Formulation.  Per level the conv is D[p, c] = sum_k X[b, k, p] * W[c, k]  (p = pixel, c = a*no + o).
+//   A operand = feature map, straight from NCHW: pixels are contiguous, so A is "MN-major"; a TMA box
+//               {64 px, 32 k} lands as [32 k-rows][128 B] with the 128-byte swizzle -- the canonical
+//               MN-major SWIZZLE_128B UMMA layout.  Two boxes make the 128-pixel M tile.
+//   B operand = packed bf16 weights [Npad, K], K-major, TMA box {32 k, Npad} with the 64-byte swizzle.
+//   D         = 128 lanes (pixels) x Npad fp32 columns in TMEM, double buffered (2 x 256 columns).
+// With pixels on TMEM lanes, one epilogue thread owns one output row (b, a, y, x, 0..no): a warp's
+// 32 rows are ONE contiguous span of z (32*no*4 bytes), staged in shared memory and written with a
+// single bulk (TMA) store.  The permute(0,1,3,4,2) of the reference therefore costs nothing.
+//
+// Warp roles (128 + 128*na threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warp 3 idle, then 4 epilogue warps per anchor (warp%4 = TMEM lane quadrant).
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
+// round-robin tile scheduler over all (level, image, 128-pixel block) tiles, heaviest level first.
 #include "yc_common.cuh"
+#include "yc_sm100.cuh"
+
 namespace yc {
-int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, cudaStream_t stream)
+
+using namespace sm100;
+
+constexpr int TC_BM = 128;       // pixels per tile (UMMA M)
+constexpr int TC_BK = 32;        // k per pipeline stage
+constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_N = 256;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 8 KB: two {64 px, 32 k} bf16 boxes
+constexpr int TC_B_BYTES_MAX = TC_MAX_N * TC_BK * 2; // 16 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES_MAX;
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_NON_EPI_THREADS = 128;
+
+struct TcLevel {
+    const float2 *sb;   // (scale, bias2) per column
+    float *raw;         // [bs, na, HW, no] or null
+    int K, HW, nx;
+    int tiles_per_img;  // ceil(HW / 128)
+    int tile_begin;     // first tile id of this level in schedule order
+    int row_off;        // first z row of this level
+    float stride;
+    float anchor_wh[YC_MAX_ANCHORS * 2];
+};
+
+struct TcParams {
+    TcLevel lv[YC_MAX_LEVELS]; // in schedule order (largest K first)
+    int n_lv;
+    int total_tiles;
+    int bs, na, no, npad;
+    int rows_total;
+    int write_z;               // 0 for YC_HEAD_RAW
+    float *z;
+    uint32_t idesc;
+    uint32_t b_bytes;          // npad * TC_BK * 2
+    uint32_t slab_bytes;       // 32 * no * 4, rounded up to 16
+};
+
+struct TcMaps {
+    CUtensorMap a[YC_MAX_LEVELS];
+    CUtensorMap b[YC_MAX_LEVELS];
+};
+
+struct TileCoord { int lv, b, p0; };
+
+__device__ __forceinline__ TileCoord tile_coord(const TcParams &P, int t)
 {
-    set_error("tcgen05 head path not built yet");
-    return YC_ERR_UNSUPPORTED;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < YC_MAX_LEVELS; ++i)
+        if (i < P.n_lv && t >= P.lv[i].tile_begin) l = i;
+    const int r = t - P.lv[l].tile_begin;
+    TileCoord c;
+    c.lv = l;
+    c.b = r / P.lv[l].tiles_per_img;
+    c.p0 = (r - c.b * P.lv[l].tiles_per_img) * TC_BM;
+    return c;
 }
+
+// Epilogue for W consecutive accumulator columns [c0, c0+W) of this thread's row.
+//   RAW:   slab[o] = t                     (pre-sigmoid map, forward()'s list `x`)
+//   !RAW:  slab[o] = decode(sigmoid(t))    (z row; o<2 xy, o<4 wh: nets/idetect.py:40-42)
+template <int W, bool RAW>
+__device__ __forceinline__ void epi_chunk(uint32_t taddr, int c0, const float2 *__restrict__ sb, float *__restrict__ srow,
+                                          float gx, float gy, float stride, float aw, float ah)
+{
+    uint32_t v[W];
+    TmemLd<W>::ld(taddr + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const float2 s_b = __ldg(sb + c0 + j); // same address for the whole warp: one broadcast load
+        const float t = fmaf(__uint_as_float(v[j]), s_b.x, s_b.y);
+        float r;
+        if (RAW) {
+            r = t;
+        } else {
+            r = sigmoidf_fast(t);
+            const int o = c0 + j;
+            if (o == 0) r = decode_xy(r, gx, stride);
+            else if (o == 1) r = decode_xy(r, gy, stride);
+            else if (o == 2) r = decode_wh(r, aw);
+            else if (o == 3) r = decode_wh(r, ah);
+        }
+        srow[c0 + j] = r;
+    }
 }
+
+template <bool RAW>
+__device__ __forceinline__ void epi_row(uint32_t taddr, int no, const float2 *__restrict__ sb, float *__restrict__ srow,
+                                        float gx, float gy, float stride, float aw, float ah)
+{
+    int c0 = 0;
+    for (; c0 + 16 <= no; c0 += 16) epi_chunk<16, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah);
+    const int rem = no - c0;
+    if (rem & 8) { epi_chunk<8, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 8; }
+    if (rem & 4) { epi_chunk<4, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 4; }
+    if (rem & 2) { epi_chunk<2, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 2; }
+    if (rem & 1) { epi_chunk<1, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); }
+}
+
+// warp-cooperative write of `nv` finished rows from the slab to global memory
+__device__ __forceinline__ void slab_store(float *__restrict__ gdst, const float *__restrict__ slab, int nv, int no, int lane)
+{
+    const uint32_t bytes = (uint32_t)nv * no * 4u;
+    fence_proxy_async_smem();
+    __syncwarp();
+    if ((((uintptr_t)gdst | bytes) & 15u) == 0) {
+        if (lane == 0) {
+            bulk_store(gdst, slab, bytes);
+            bulk_commit();
+        }
+    } else { // unaligned span (odd shapes): plain coalesced stores
+        for (int i = lane; i < nv * no; i += 32) gdst[i] = slab[i];
+    }
+}
+
+__global__ void __launch_bounds__(TC_NON_EPI_THREADS + 128 * 3, 1)
+head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // carve: [stages: A|B] (1024-aligned) [slabs] [barriers]
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *stage_base = smem;
+    float *slabs = (float *)(smem + TC_STAGES * TC_STAGE_BYTES);
+    const int n_epi_warps = 4 * P.na;
+    uint64_t *bars = (uint64_t *)((uint8_t *)slabs + (size_t)n_epi_warps * P.slab_bytes);
+    uint64_t *full_bar = bars;                    // [TC_STAGES]
+    uint64_t *empty_bar = bars + TC_STAGES;       // [TC_STAGES]
+    uint64_t *tfull_bar = bars + 2 * TC_STAGES;   // [2]
+    uint64_t *tempty_bar = bars + 2 * TC_STAGES + 2; // [2]
+    uint32_t *tmem_ptr_smem = (uint32_t *)(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < P.n_lv; ++i) {
+            prefetch_tmap(&maps.a[i]);
+            prefetch_tmap(&maps.b[i]);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], (uint32_t)n_epi_warps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr_smem, TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+                const TileCoord tc = tile_coord(P, t);
+                const int nkb = (P.lv[tc.lv].K + TC_BK - 1) / TC_BK;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t *sa = stage_base + stage * TC_STAGE_BYTES, *sb = sa + TC_A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)TC_A_BYTES + P.b_bytes);
+                    tma_load_3d(sa, &maps.a[tc.lv], &full_bar[stage], tc.p0, kb * TC_BK, tc.b);
+                    tma_load_3d(sa + TC_A_BYTES / 2, &maps.a[tc.lv], &full_bar[stage], tc.p0 + 64, kb * TC_BK, tc.b);
+                    tma_load_2d(sb, &maps.b[tc.lv], &full_bar[stage], kb * TC_BK, 0);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected lane) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+                const TileCoord tc = tile_coord(P, t);
+                const int nkb = (P.lv[tc.lv].K + TC_BK - 1) / TC_BK;
+                const int buf = it & 1;
+                mbar_wait(&tempty_bar[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u); // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_MAX_N;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_addr(stage_base + stage * TC_STAGE_BYTES), sb = sa + TC_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        // A: MN-major SW128: 64-px chunks LBO = 4096 B apart, 8-k groups SBO = 1024 B apart;
+                        //    one k16 step = two 8-k groups = 2048 B
+                        const uint64_t da = smem_desc(sa + k * 2048, TC_A_BYTES / 2, 1024, SWZ_128B);
+                        // B: K-major SW64: 8-row groups SBO = 512 B apart; k16 step = 32 B inside the 64-B row
+                        const uint64_t db = smem_desc(sb + k * 32, 16, 512, SWZ_64B);
+                        mma_f16(tmem_d, da, db, P.idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    mma_commit(&empty_bar[stage]); // frees the smem slot when these MMAs retire
+                    if (kb == nkb - 1) mma_commit(&tfull_bar[buf]);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= TC_NON_EPI_THREADS / 32) {
+        // ===================== epilogue: TMEM -> sigmoid/decode -> slab -> bulk store =====================
+        const int e = warp - TC_NON_EPI_THREADS / 32;
+        const int q = warp & 3;     // TMEM lane quadrant this warp may read
+        const int a = e >> 2;       // anchor handled by this warp
+        float *slab = (float *)((uint8_t *)slabs + (size_t)e * P.slab_bytes);
+        float *srow = slab + lane * P.no;
+        const int no = P.no;
+        int it = 0;
+        for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+            const TileCoord tc = tile_coord(P, t);
+            const TcLevel &L = P.lv[tc.lv];
+            const int buf = it & 1;
+            const int prow0 = tc.p0 + 32 * q;            // first pixel of this warp's 32 rows
+            const int nv = min(32, L.HW - prow0);        // valid rows (<= 0: nothing to store)
+            const int p = prow0 + lane;
+            const float gx = (float)(p % L.nx), gy = (float)(p / L.nx);
+            const float aw = L.anchor_wh[2 * a], ah = L.anchor_wh[2 * a + 1];
+            const float2 *sb = L.sb + a * no;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_MAX_N + a * no);
+
+            mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            if (L.raw) {
+                if (lane == 0) bulk_wait_read0(); // previous store from this slab has been read out
+                __syncwarp();
+                epi_row<true>(taddr, no, sb, srow, gx, gy, L.stride, aw, ah);
+                if (nv > 0)
+                    slab_store(L.raw + (((size_t)tc.b * P.na + a) * L.HW + prow0) * no, slab, nv, no, lane);
+            }
+            if (P.write_z) {
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+                epi_row<false>(taddr, no, sb, srow, gx, gy, L.stride, aw, ah);
+            }
+            // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (P.write_z && nv > 0)
+                slab_store(P.z + ((size_t)tc.b * P.rows_total + L.row_off + (size_t)a * L.HW + prow0) * no, slab, nv, no,
+                           lane);
+        }
+        if (lane == 0) bulk_wait_all0(); // global writes complete before the CTA exits
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int g_num_sms = 0;
+
+int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, unsigned *left_mask,
+                        cudaStream_t stream)
+{
+    const int N = d->na * d->no, npad = round_up(N, 16);
+    YC_REQUIRE(d->x_dtype == YC_BF16, YC_ERR_UNSUPPORTED, "tcgen05 head: feature maps must be bf16 (fp32 maps use the exact FFMA path)");
+    YC_REQUIRE(d->kind == YC_HEAD_IDETECT || d->kind == YC_HEAD_RAW, YC_ERR_UNSUPPORTED,
+               "tcgen05 head: kind %d not supported yet", d->kind);
+    YC_REQUIRE(npad <= TC_MAX_N && d->na <= 3, YC_ERR_UNSUPPORTED, "tcgen05 head: na*no=%d (na=%d) exceeds one 256-column tile",
+               N, d->na);
+    EncodeTiledFn enc = encode_tiled();
+    YC_REQUIRE(enc != nullptr, YC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+
+    const uint32_t slab_bytes = (uint32_t)round_up(32 * d->no * 4, 16);
+    const size_t smem_bytes = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)4 * d->na * slab_bytes + 256;
+    YC_REQUIRE(smem_bytes <= 227 * 1024, YC_ERR_UNSUPPORTED, "tcgen05 head: needs %zu bytes of shared memory", smem_bytes);
+
+    // which levels fit: TMA needs 16-byte aligned bases and row pitches
+    unsigned fit = 0;
+    for (int i = 0; i < d->nl; ++i) {
+        const yc_head_level &lv = d->level[i];
+        const size_t HW = (size_t)lv.H * lv.W;
+        const bool ok = (HW * 2) % 16 == 0 && ((size_t)lv.K * 2) % 16 == 0 && ((uintptr_t)lv.x & 15) == 0 &&
+                        (d->kind != YC_HEAD_RAW || lv.raw);
+        if (ok) fit |= 1u << i;
+        else set_error("level %d (K=%d, H*W=%zu) does not meet the TMA alignment rules", i, lv.K, HW);
+    }
+    *left_mask = ((1u << d->nl) - 1u) & ~fit;
+    if (!fit) return YC_ERR_UNSUPPORTED;
+
+    // schedule order: largest K first (longest tiles first)
+    int order[YC_MAX_LEVELS], n = 0;
+    for (int i = 0; i < d->nl; ++i)
+        if (fit >> i & 1u) order[n++] = i;
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j)
+            if (d->level[order[j]].K > d->level[order[i]].K) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+
+    TcMaps maps;
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_lv = n;
+    P.bs = d->bs; P.na = d->na; P.no = d->no; P.npad = npad;
+    P.rows_total = rows_total;
+    P.write_z = d->kind == YC_HEAD_IDETECT ? 1 : 0;
+    P.z = d->z;
+    P.idesc = instr_desc_f16(/*bf16*/ 1, /*A MN-major*/ 1, /*B K-major*/ 0, TC_BM, (uint32_t)npad);
+    P.b_bytes = (uint32_t)npad * TC_BK * 2;
+    P.slab_bytes = slab_bytes;
+    int tiles = 0;
+    for (int s = 0; s < n; ++s) {
+        const int i = order[s];
+        const yc_head_level &lv = d->level[i];
+        const int HW = lv.H * lv.W;
+        BlobView bv = blob_view(lv.blob, N, lv.K);
+        TcLevel &L = P.lv[s];
+        L.sb = bv.sb;
+        L.raw = lv.raw;
+        L.K = lv.K; L.HW = HW; L.nx = lv.W;
+        L.tiles_per_img = (HW + TC_BM - 1) / TC_BM;
+        L.tile_begin = tiles;
+        L.row_off = row_off[i];
+        L.stride = lv.stride;
+        for (int j = 0; j < YC_MAX_ANCHORS * 2; ++j) L.anchor_wh[j] = lv.anchor_wh[j];
+        tiles += d->bs * L.tiles_per_img;
+        {   // A: X [bs, K, HW] bf16, box {64 px, 32 k, 1}
+            cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)lv.K, (cuuint64_t)d->bs};
+            cuuint64_t gstr[2] = {(cuuint64_t)HW * 2, (cuuint64_t)HW * lv.K * 2};
+            cuuint32_t box[3] = {64, TC_BK, 1}, est[3] = {1, 1, 1};
+            CUresult r = enc(&maps.a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)lv.x, gdim, gstr, box, est,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            YC_REQUIRE(r == CUDA_SUCCESS, YC_ERR_CUDA, "cuTensorMapEncodeTiled(A, level %d) failed: %d", i, (int)r);
+        }
+        {   // B: W [Npad, K] bf16, box {32 k, Npad}
+            cuuint64_t gdim[2] = {(cuuint64_t)lv.K, (cuuint64_t)npad};
+            cuuint64_t gstr[1] = {(cuuint64_t)lv.K * 2};
+            cuuint32_t box[2] = {TC_BK, (cuuint32_t)npad}, est[2] = {1, 1};
+            CUresult r = enc(&maps.b[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)bv.w_bf, gdim, gstr, box, est,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            YC_REQUIRE(r == CUDA_SUCCESS, YC_ERR_CUDA, "cuTensorMapEncodeTiled(B, level %d) failed: %d", i, (int)r);
+        }
+    }
+    P.total_tiles = tiles;
+
+    if (!g_num_sms) {
+        int dev = 0;
+        YC_CUDA(cudaGetDevice(&dev));
+        YC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        YC_CUDA(cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    head_tc_kernel<<<grid, TC_NON_EPI_THREADS + 128 * d->na, smem_bytes, stream>>>(maps, P);
+    YC_CUDA(cudaGetLastError());
+    return YC_OK;
+}
+
+} // namespace yc

@@ -123,22 +123,60 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar)
 
 // TMEM -> registers: this warp's 32 lanes x W consecutive 32-bit columns
 template <int W> struct TmemLd;
-#define YC_TMEM_LD_BODY(W_, REGS, OUTS)                                                                       \
-    template <> struct TmemLd<W_> {                                                                           \
-        static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)                                \
-        {                                                                                                     \
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x" #W_ ".b32 {" REGS "}, [%" #W_ "];" : OUTS : "r"(taddr) : "memory"); \
-        }                                                                                                     \
-    };
-YC_TMEM_LD_BODY(1, "%0", "=r"(r[0]))
-YC_TMEM_LD_BODY(2, "%0, %1", "=r"(r[0]), "=r"(r[1]))
-YC_TMEM_LD_BODY(4, "%0, %1, %2, %3", "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]))
-YC_TMEM_LD_BODY(8, "%0, %1, %2, %3, %4, %5, %6, %7",
-                "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]))
-YC_TMEM_LD_BODY(16, "%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15",
-                "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]))
-#undef YC_TMEM_LD_BODY
+template <> struct TmemLd<1> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];"
+                     : "=r"(r[0])
+                     : "r"(taddr)
+                     : "memory");
+    }
+};
+template <> struct TmemLd<2> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                     : "=r"(r[0]), "=r"(r[1])
+                     : "r"(taddr)
+                     : "memory");
+    }
+};
+template <> struct TmemLd<4> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                     : "r"(taddr)
+                     : "memory");
+    }
+};
+template <> struct TmemLd<8> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr)
+                     : "memory");
+    }
+};
+template <> struct TmemLd<16> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr)
+                     : "memory");
+    }
+};
+template <> struct TmemLd<32> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr)
+                     : "memory");
+    }
+};
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp layouts, rebuilt from the bit fields) -----------
