@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- post-backbone images/sec of the B200 path (and the reference's CPU path beside it).
+
+Workload (BASELINE.json configs[1], "C2"): yolov7 COCO IDetect head (80 classes, 3 anchors x 3 strides,
+ch 256/512/1024) at 640x640, batch 64 per GPU, synthetic feature maps, seeded trained-like weights,
+conf 0.25 / iou 0.45.  One "step" = one pass of the hot path over one batch:
+    head 1x1 conv (+ImplicitA/M) -> sigmoid + box decode -> conf threshold + compaction -> per-class NMS
+    -> letterbox undo.
+`value` is measured with inputs resident in HBM; `e2e` goes through the host-buffer call
+(PostBackbone.run_host: H2D of the feature maps + the step + D2H of the detections).
+N > 1: weak scaling, each rank owns its own 64 images; one NCCL all-gather of detections per step.
+`--impl reference` times the reference's own CPU path (oracle/ref_port.py, the torch-CPU port; the
+reference is pure Python and /root/reference does not travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+COCO_ANCHORS = [[12, 16, 19, 36, 40, 28], [36, 75, 76, 55, 72, 146], [142, 110, 192, 243, 459, 401]]
+CH = (256, 512, 1024)
+SHAPES = [(80, 80), (40, 40), (20, 20)]
+STRIDES = [8.0, 16.0, 32.0]
+NC = 80
+CONF, IOU = 0.25, 0.45
+INPUT_SHAPE, IMAGE_SHAPE = (640, 640), (512, 773)
+BYTES_PER_IMG = {"bf16": 2867200 * 2 + 25200 * 85 * 4, "fp32": 2867200 * 4 + 25200 * 85 * 4}  # S1: maps in + z out
+FLOPS_PER_IMG = 2 * 255 * 2867200
+
+
+def make_head(seed=0):
+    """IDetect with seeded 'trained-like' parameters: box rows N(0,.02) as
+    Model.initial_weights (nets/yolo.py:120); obj/cls rows scaled so that logits are ~N(-5,1.5) /
+    N(-3,1.5); ia ~ N(0,.02); im ~ N(1,.02)."""
+    import torch
+    from yolo_continuous_b200.nets import IDetect
+    g = torch.Generator().manual_seed(seed)
+    head = IDetect(NC, COCO_ANCHORS, CH).eval()
+    with torch.no_grad():
+        for i, conv in enumerate(head.m):
+            k = conv.weight.shape[1]
+            w = torch.randn(conv.weight.shape, generator=g) * 0.02
+            wv = w.view(head.na, head.no, k)
+            wv[:, 4:, :] = torch.randn(head.na, head.no - 4, k, generator=g) * (1.5 / k ** 0.5)
+            conv.weight.copy_(w)
+            b = torch.zeros(head.na, head.no)
+            b[:, 4], b[:, 5:] = -5.0, -3.0
+            conv.bias.copy_(b.view(-1))
+            head.ia[i].implicit.copy_(torch.randn(head.ia[i].implicit.shape, generator=g) * 0.02)
+            head.im[i].implicit.copy_(1.0 + torch.randn(head.im[i].implicit.shape, generator=g) * 0.02)
+    head.stride = torch.tensor(STRIDES)
+    return head
+
+
+def port_params(head):
+    return {"anchors": head.anchor_grid.detach().cpu().reshape(3, -1, 2).numpy(),
+            "w": [m.weight.detach().cpu()[:, :, 0, 0] for m in head.m], "b": [m.bias.detach().cpu() for m in head.m],
+            "ia": [a.implicit.detach().cpu().reshape(-1) for a in head.ia],
+            "im": [m.implicit.detach().cpu().reshape(-1) for m in head.im]}
+
+
+def time_cpu_port(head, bs, iters, warmup, seed=1234):
+    """The reference's CPU path (torch-CPU port) on `bs` images of the workload; returns img/s, cores."""
+    import torch
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(seed)
+    xs = [torch.randn(bs, c, h, w, generator=g).to(torch.bfloat16).float() for c, (h, w) in zip(CH, SHAPES)]
+    p = port_params(head)
+    ts = []
+    with torch.no_grad():
+        for it in range(warmup + iters):
+            t0 = time.perf_counter()
+            ref_port.post_backbone(p, [x.clone() for x in xs], STRIDES, NC, INPUT_SHAPE, IMAGE_SHAPE, True, CONF, IOU)
+            if it >= warmup:
+                ts.append(time.perf_counter() - t0)
+    return bs / statistics.median(ts), cores, statistics.median(ts)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    head = make_head()
+    bs = 4
+    ips, cores, sec = time_cpu_port(head, bs, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "post_backbone_images_per_sec", "value": ips, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(bs, "f32"),
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"{bs} images per step of the C2 workload, torch CPU ops, {cores} threads"},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(bs, dtype):
+    return {"workload": "C2: yolov7 COCO IDetect head (nc=80, 3 anchors x strides 8/16/32, ch 256/512/1024) decode+NMS, "
+                        "640x640, synthetic feature maps", "batch_per_gpu": bs, "rows_per_image": 25200,
+            "conf_thres": CONF, "nms_thres": IOU, "feature_dtype": dtype,
+            "l2": "inputs larger than L2 (feature maps %.0f MB per step)" % (bs * 2867200 * (2 if dtype == "bf16" else 4) / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bs", type=int, default=64)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="device-resident loop only (for ncu runs)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from yolo_continuous_b200 import _lib
+    from yolo_continuous_b200.parallel import gather_detections
+    from yolo_continuous_b200.pipeline import PostBackbone
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.check(_lib.lib.yc_device_check(local), "yc_device_check")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    head = make_head().to(dev)
+    pipe = PostBackbone(head, args.bs, SHAPES, tdt, INPUT_SHAPE, IMAGE_SHAPE, True, CONF, IOU, dev, use_graph=False)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    xs = [torch.randn(args.bs, c, h, w, generator=g, device=dev).to(tdt) for c, (h, w) in zip(CH, SHAPES)]
+    for d_, h_ in zip(xs, pipe.x_host):
+        h_.copy_(d_)
+
+    def step():
+        rows, _, counts, offsets = pipe.run_device(xs)
+        if world > 1:
+            gather_detections(rows, counts)
+        return rows, counts, offsets
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput: K steps between two events, head kernel bracketed by its own events ----
+    for _ in range(W):
+        step()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    sync_all()
+    t0.record()
+    for i in range(K):
+        # same launches as pipe.run_device, with the head kernel bracketed on its own stream
+        for j, x in enumerate(xs):
+            pipe.desc.level[j].x = x.data_ptr()
+        s = _lib.stream_ptr(dev)
+        ev[i][0].record()
+        _lib.check(_lib.lib.yc_head_forward(pipe.desc, s), "yc_head_forward")
+        ev[i][1].record()
+        m = pipe.meta.data_ptr()
+        _lib.check(_lib.lib.yc_nms_batched(pipe.z.data_ptr(), pipe.nms_params, pipe.ws.data_ptr(), pipe.ws.numel(),
+                                           pipe.out_rows.data_ptr(), pipe.out_idx.data_ptr(), m, m + 4 * args.bs, s),
+                   "yc_nms_batched")
+        if world > 1:
+            gather_detections(pipe.out_rows, pipe.meta[:args.bs])
+    t1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms = t0.elapsed_time(t1)
+    head_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.bs * K / (ms / 1e3)
+    counts_host = pipe.meta[:args.bs].cpu().numpy()
+    n_det = int(counts_host.sum())
+
+    if args.profile:
+        print(json.dumps({"profile_run": True, "value": value, "ms_per_step": ms / K, "head_ms": head_ms}))
+        return
+
+    # ---- end to end through the host-buffer call ------------------------------------------------------------
+    for _ in range(3):
+        pipe.run_host()
+    sync_all()
+    e0 = time.perf_counter()
+    total_rows = 0
+    for _ in range(K):
+        out = pipe.run_host()
+        if world > 1:
+            gather_detections(pipe.out_rows, pipe.meta[:args.bs])
+    torch.cuda.synchronize()
+    e_ms = (time.perf_counter() - e0) * 1e3
+    total_rows = sum(0 if o is None else len(o) for o in out)
+    if world > 1:
+        t = torch.tensor([e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+    e2e_value = world * args.bs * K / (e_ms / 1e3)
+
+    # ---- NMS latency at batch 1 (second metric of BASELINE.json) ---------------------------------------------
+    nms_p50 = None
+    if rank == 0:
+        from yolo_continuous_b200 import detect
+        z1 = pipe.z[:1].clone()
+        lat = []
+        for i in range(60):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            detect.nms_device(z1, NC, CONF, IOU, INPUT_SHAPE, IMAGE_SHAPE, True, write_corners=False)
+            b.record()
+            b.synchronize()
+            if i >= 10:
+                lat.append(a.elapsed_time(b))
+        nms_p50 = statistics.median(lat)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = {}, "fallback"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_src = "measured"
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_launch = BYTES_PER_IMG[args.dtype] * args.bs
+    achieved = bytes_launch / (head_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"head_{args.dtype}_bs{args.bs}")
+    except (OSError, ValueError):
+        pass
+    line = {
+        "metric": "post_backbone_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
+        "config": workload_config(args.bs, args.dtype),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
+                "d2h_bytes_per_step": pipe.d2h_bytes(total_rows), "ms_per_step": e_ms / K},
+        "gpu_launches": K * pipe.kernels_per_step,
+        "roofline": {"kernel": "head_tc_kernel" if args.dtype == "bf16" else "head_generic_kernel", "bound": "hbm",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_launch,
+                     "kernel_ms": head_ms, "kernel_share_of_step": head_ms / (ms / K),
+                     "tensor_tflops": FLOPS_PER_IMG * args.bs / (head_ms / 1e3) / 1e12},
+        "detections_per_step": n_det, "nms_p50_ms_per_image_bs1": nms_p50,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ips, cores, sec = time_cpu_port(make_head(), 8, 3, 1)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"8 images of the same workload, 3 timed passes (median {sec:.2f} s), "
+                                          f"torch CPU ops with {cores} threads"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

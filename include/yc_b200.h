@@ -120,6 +120,9 @@ typedef struct yc_nms_params {
     int32_t input_h, input_w;
     const int32_t *image_hw;      /* device [bs,2] original image h,w (or [1,2] with image_hw_stride 0) */
     int32_t image_hw_stride;      /* 2 or 0 */
+    float box_div_w, box_div_h;   /* when > 0: cx,w /= box_div_w and cy,h /= box_div_h (IEEE division) before the
+                                     corners are formed -- turns IDetect's input-pixel boxes into the normalised
+                                     boxes yolo_correct_boxes expects; 0 = off */
 } yc_nms_params;
 
 YC_API size_t yc_nms_workspace_bytes(int bs, int rows, int nc);

@@ -85,3 +85,24 @@ def test_bbox_known_answers():
     with pytest.raises(Exception):
         orc.cvt_bbox(fx["boxes"], 6)
     assert np.array_equal(orc.box_iou(fx["iou_b1"], fx["iou_b2"]), fx["iou"])
+
+
+def test_torch_port_matches_reference_bit_exact():
+    """oracle/ref_port.py (the CPU-baseline port) reproduces the reference's outputs exactly."""
+    import torch
+    from oracle import ref_port
+    fx = load("idetect_nc80")
+    p = head_params(fx, "idetect")
+    z, raws = ref_port.idetect_forward(p, [fx[f"x{i}"] for i in range(3)], fx["strides"])
+    assert np.array_equal(z.numpy(), fx["z"])
+    for i in range(3):
+        assert np.array_equal(raws[i].numpy(), fx[f"raw{i}"])
+    for name in ("nms_clustered_lb", "nms_clustered_nolb", "nms_with_none", "nms_thr_round"):
+        fx = load(name)
+        out = ref_port.non_max_suppression(torch.from_numpy(fx["pred"].copy()), int(fx["nc"]), tuple(fx["input_shape"]),
+                                           np.array(fx["image_shape"]), bool(fx["letterbox"]), float(fx["conf"]),
+                                           float(fx["iou"]))
+        rows = [o for o in out if o is not None]
+        got = np.concatenate(rows, 0) if rows else np.zeros((0, 7), np.float32)
+        assert np.array_equal(got, fx["rows"].astype(np.float32))
+        assert [0 if o is None else len(o) for o in out] == fx["counts"].tolist()

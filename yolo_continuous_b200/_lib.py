@@ -32,7 +32,8 @@ class NmsParams(C.Structure):
                 ("conf_thres", C.c_float), ("nms_thres", C.c_double),
                 ("write_corners", C.c_int32), ("correct_boxes", C.c_int32), ("letterbox", C.c_int32),
                 ("input_h", C.c_int32), ("input_w", C.c_int32),
-                ("image_hw", C.c_void_p), ("image_hw_stride", C.c_int32)]
+                ("image_hw", C.c_void_p), ("image_hw_stride", C.c_int32),
+                ("box_div_w", C.c_float), ("box_div_h", C.c_float)]
 
 
 EXPORTS = ["yc_last_error", "yc_version", "yc_device_check", "yc_head_pack_bytes", "yc_head_pack",

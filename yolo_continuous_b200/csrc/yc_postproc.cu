@@ -105,7 +105,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // 16-byte aligned, so HBM sees full-line requests; each thread then owns one row
 // (stride-row_stride reads are bank-conflict free for odd row_stride such as 85).
 __global__ void __launch_bounds__(TC_ROWS) threshold_compact_kernel(float *__restrict__ pred, int rows, int row_stride,
-                                                                    int nc, float conf, int write_corners, NmsWs ws)
+                                                                    int nc, float conf, int write_corners, float div_w,
+                                                                    float div_h, NmsWs ws)
 {
     extern __shared__ __align__(128) float tile[];
     __shared__ __align__(8) uint64_t bar;
@@ -132,7 +133,10 @@ __global__ void __launch_bounds__(TC_ROWS) threshold_compact_kernel(float *__res
     float x1 = 0, y1 = 0, x2 = 0, y2 = 0, obj = 0, bv = 0, score = 0;
     if (tid < m) {
         const float *q = tile + tid * row_stride;
-        const float cx = q[0], cy = q[1], hw = __fmul_rn(q[2], 0.5f), hh = __fmul_rn(q[3], 0.5f);
+        float cx = q[0], cy = q[1], bw = q[2], bh = q[3];
+        if (div_w > 0.f) { cx = __fdiv_rn(cx, div_w); bw = __fdiv_rn(bw, div_w); }
+        if (div_h > 0.f) { cy = __fdiv_rn(cy, div_h); bh = __fdiv_rn(bh, div_h); }
+        const float hw = __fmul_rn(bw, 0.5f), hh = __fmul_rn(bh, 0.5f);
         x1 = __fsub_rn(cx, hw); y1 = __fsub_rn(cy, hh);
         x2 = __fadd_rn(cx, hw); y2 = __fadd_rn(cy, hh);
         obj = q[4];
@@ -515,7 +519,7 @@ extern "C" int yc_nms_batched(float *pred, const yc_nms_params *p, void *workspa
                                      (int)tile_bytes));
     dim3 g1((p->rows + TC_ROWS - 1) / TC_ROWS, p->bs);
     threshold_compact_kernel<<<g1, TC_ROWS, tile_bytes, stream>>>(pred, p->rows, p->row_stride, p->nc, p->conf_thres,
-                                                                  p->write_corners, ws);
+                                                                  p->write_corners, p->box_div_w, p->box_div_h, ws);
     segment_offsets_kernel<<<p->bs, 256, 0, stream>>>(p->nc, ws);
     bucket_scatter_kernel<<<dim3((p->rows + 255) / 256, p->bs), 256, 0, stream>>>(p->rows, p->nc, ws);
     nms_segment_kernel<<<dim3(p->nc, p->bs), NMS_NT, 0, stream>>>(p->rows, p->nc, thr_to_f32_floor(p->nms_thres), ws);

@@ -1,0 +1,138 @@
+"""Post-backbone pipeline with preallocated buffers: neck feature maps -> detections.
+
+This is the batched, allocation-free form of what reference detect.predict does after the
+backbone (detect.py:227-234): head (conv + implicit + decode) -> threshold/compaction -> per-class
+NMS -> letterbox undo.  Two entry points:
+
+* run_device(features): inputs already on the device; results stay on the device.  The whole step
+  (1 head kernel + the NMS kernels) can be replayed as one CUDA graph.
+* run_host(features_host): the user-facing call with HOST buffers -- pinned host feature maps are
+  copied to the device, the step runs, and the per-image detection arrays are copied back.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class PostBackbone:
+    def __init__(self, head, bs, shapes, dtype=torch.bfloat16, input_shape=(640, 640), image_shape=(640, 640),
+                 letterbox_image=True, conf_thres=0.25, nms_thres=0.45, device="cuda:0", use_graph=True,
+                 spec_rows=65536):
+        self.head, self.bs, self.shapes = head, bs, [tuple(s) for s in shapes]
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.nc, self.na, self.no = head.nc, head.na, head.no
+        if not hasattr(head, "m") or head.no != head.nc + 5:
+            raise _lib.YcError("PostBackbone drives IDetect/IAuxDetect-style heads (no = nc + 5)")
+        self.nl = len(self.shapes)
+        dev = self.device
+        self.rows = sum(self.na * h * w for h, w in self.shapes)
+        self.ch = [head.m[i].weight.shape[1] for i in range(self.nl)]
+        with torch.cuda.device(dev):
+            self.x_dev = [torch.empty((bs, c, h, w), dtype=dtype, device=dev) for c, (h, w) in zip(self.ch, self.shapes)]
+            self.z = torch.empty((bs, self.rows, self.no), dtype=torch.float32, device=dev)
+            self.out_rows = torch.empty((bs * self.rows, 7), dtype=torch.float32, device=dev)
+            self.out_idx = torch.empty((bs * self.rows,), dtype=torch.int32, device=dev)
+            # counts [bs] and offsets [bs+1] share one buffer so that a single D2H copy fetches both
+            self.meta = torch.empty((2 * bs + 1,), dtype=torch.int32, device=dev)
+            self.ws = torch.empty(_lib.lib.yc_nms_workspace_bytes(bs, self.rows, self.nc) + 1024, dtype=torch.uint8,
+                                  device=dev)
+            hw = np.asarray(image_shape, dtype=np.int32).reshape(-1, 2)
+            self.image_hw = torch.from_numpy(np.ascontiguousarray(hw)).to(dev)
+            self.x_host = [torch.empty(t.shape, dtype=dtype).pin_memory() for t in self.x_dev]
+            self.spec_rows = min(spec_rows, bs * self.rows)
+            self.meta_host = torch.empty((2 * bs + 1,), dtype=torch.int32).pin_memory()
+            self.rows_host = torch.empty((bs * self.rows, 7), dtype=torch.float32).pin_memory() \
+                if bs * self.rows <= (1 << 22) else torch.empty((1 << 22, 7), dtype=torch.float32).pin_memory()
+        # descriptors (pointers filled per call for the head inputs)
+        d = _lib.HeadDesc()
+        d.kind, d.path = _lib.YC_HEAD_IDETECT, head.head_path
+        d.x_dtype = _lib.YC_BF16 if dtype == torch.bfloat16 else _lib.YC_F32
+        d.nl, d.na, d.no, d.bs = self.nl, self.na, self.no, bs
+        self._blobs = []
+        for i, (h, w) in enumerate(self.shapes):
+            blob = head._blob((id(head.m[i]),), head.m[i], head.ia[i], head.im[i], dev)
+            self._blobs.append(blob)
+            lv = d.level[i]
+            lv.blob, lv.K, lv.H, lv.W = blob.data_ptr(), self.ch[i], h, w
+            lv.stride = float(head.stride[i])
+            for j, v in enumerate(head.anchor_grid[i].reshape(-1).tolist()):
+                lv.anchor_wh[j] = v
+        d.z = self.z.data_ptr()
+        self.desc = d
+        p = _lib.NmsParams()
+        p.bs, p.rows, p.row_stride, p.nc = bs, self.rows, self.no, self.nc
+        p.conf_thres, p.nms_thres = float(conf_thres), float(nms_thres)
+        p.write_corners, p.correct_boxes, p.letterbox = 0, 1, 1 if letterbox_image else 0
+        p.input_h, p.input_w = int(input_shape[0]), int(input_shape[1])
+        p.image_hw, p.image_hw_stride = self.image_hw.data_ptr(), (2 if hw.shape[0] > 1 else 0)
+        p.box_div_w, p.box_div_h = float(input_shape[1]), float(input_shape[0])
+        self.nms_params = p
+        self.kernels_per_step = 1 + 6   # head_tc_kernel + 6 post-processing kernels (memset is not a kernel)
+        self.graph = None
+        self.use_graph = use_graph
+        self._graph_ptrs = None
+
+    # ---- device path -----------------------------------------------------------------------
+    def _launch(self, features):
+        for i, x in enumerate(features):
+            if x.dtype != self.dtype or tuple(x.shape) != tuple(self.x_dev[i].shape) or not x.is_contiguous():
+                raise _lib.YcError(f"level {i}: expected contiguous {tuple(self.x_dev[i].shape)} {self.dtype}")
+            self.desc.level[i].x = x.data_ptr()
+        s = _lib.stream_ptr(self.device)
+        _lib.check(_lib.lib.yc_head_forward(C.byref(self.desc), s), "yc_head_forward")
+        m = self.meta.data_ptr()
+        _lib.check(_lib.lib.yc_nms_batched(self.z.data_ptr(), C.byref(self.nms_params), self.ws.data_ptr(),
+                                           self.ws.numel(), self.out_rows.data_ptr(), self.out_idx.data_ptr(),
+                                           m, m + 4 * self.bs, s), "yc_nms_batched")
+
+    def run_device(self, features):
+        """features: list of [bs, ch_i, H_i, W_i] device tensors.  Returns device views
+        (rows [bs*rows,7] capacity, idx, counts [bs], offsets [bs+1])."""
+        with torch.cuda.device(self.device):
+            ptrs = tuple(x.data_ptr() for x in features)
+            if not self.use_graph:
+                self._launch(features)
+            else:
+                if self.graph is None or self._graph_ptrs != ptrs:
+                    self._launch(features)          # warm-up outside capture (lazy module/attribute setup)
+                    torch.cuda.current_stream().synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch(features)
+                    self.graph, self._graph_ptrs = g, ptrs
+                self.graph.replay()
+        bs = self.bs
+        return self.out_rows, self.out_idx, self.meta[:bs], self.meta[bs:]
+
+    # ---- host path (the e2e call) -----------------------------------------------------------------
+    def run_host(self, features_host=None):
+        """features_host: list of pinned host tensors (default: self.x_host).  Returns the reference's
+        result type: list with None or ndarray[n,7] (y1,x1,y2,x2 px, obj, class_conf, class_id) per image."""
+        src = self.x_host if features_host is None else features_host
+        with torch.cuda.device(self.device):
+            for d_, h_ in zip(self.x_dev, src):
+                d_.copy_(h_, non_blocking=True)
+            rows, _, _, _ = self.run_device(self.x_dev)
+            self.meta_host.copy_(self.meta, non_blocking=True)
+            spec = self.spec_rows
+            self.rows_host[:spec].copy_(rows[:spec], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            off = self.meta_host[self.bs:].numpy()
+            total = int(off[-1])
+            if total > spec:
+                if total > self.rows_host.shape[0]:
+                    raise _lib.YcError("detections exceed the pinned host buffer")
+                self.rows_host[spec:total].copy_(rows[spec:total], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        host = self.rows_host.numpy()
+        return [None if off[b + 1] == off[b] else host[off[b]:off[b + 1]].copy() for b in range(self.bs)]
+
+    def h2d_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.x_host)
+
+    def d2h_bytes(self, total_rows):
+        return self.meta_host.numel() * 4 + max(self.spec_rows, total_rows) * 28
