@@ -131,6 +131,14 @@ YC_API size_t yc_nms_workspace_bytes(int bs, int rows, int nc);
 YC_API int yc_nms_batched(float *pred, const yc_nms_params *p, void *workspace, size_t workspace_bytes, float *out_rows,
                    int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets, yc_stream_t stream);
 
+/* Fully fused step: head conv -> (epilogue) sigmoid/decode of box+objectness, class max, obj*cls >= conf,
+ * candidate emission -> per-class NMS -> letterbox undo.  z is never materialised: HBM sees the feature
+ * maps once and the detections.  Same results as yc_head_forward followed by yc_nms_batched (same arithmetic,
+ * same tie rules).  Replaces the sequence reference detect.py:227-234 for I*Detect heads.  Needs the tcgen05
+ * path for every level (bf16 maps); YC_ERR_UNSUPPORTED otherwise.  p->rows / nc must match the head. */
+YC_API int yc_detect_fused(const yc_head_desc *desc, const yc_nms_params *p, void *workspace, size_t workspace_bytes,
+                    float *out_rows, int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets, yc_stream_t stream);
+
 /* torchvision.ops.nms drop-in for one box set (detect.py:133): boxes [n,4] xyxy, scores [n].
  * keep [n] receives kept indices in score order, *keep_count_dev their number. workspace from
  * yc_nms_workspace_bytes(1, n, 1). */

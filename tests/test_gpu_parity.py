@@ -396,3 +396,90 @@ def test_tcgen05_head_full_size_vs_generic_kernel():
         assert float((a_ - b_).abs().max()) < 1e-4
     rel = (z_t - z_g).abs() / z_g.abs().clamp_min(8.0)
     assert float(rel.max()) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused step (yc_detect_fused): candidates emitted from the GEMM epilogue, z never written
+# ---------------------------------------------------------------------------------------------------
+def _bench_like_head(nc, ch, seed):
+    from yolo_continuous_b200.nets import IDetect
+    g = torch.Generator().manual_seed(seed)
+    head = IDetect(nc, COCO, ch).eval()
+    with torch.no_grad():
+        for i, conv in enumerate(head.m):
+            k = conv.weight.shape[1]
+            w = torch.randn(conv.weight.shape, generator=g) * 0.02
+            w.view(head.na, head.no, k)[:, 4:, :] = torch.randn(head.na, head.no - 4, k, generator=g) * (1.5 / k ** 0.5)
+            conv.weight.copy_(w)
+            b = torch.zeros(head.na, head.no)
+            b[:, 4], b[:, 5:] = -3.0, -2.0
+            conv.bias.copy_(b.view(-1))
+            head.ia[i].implicit.copy_(torch.randn(head.ia[i].implicit.shape, generator=g) * 0.02)
+            head.im[i].implicit.copy_(1.0 + torch.randn(head.im[i].implicit.shape, generator=g) * 0.02)
+    head.stride = torch.tensor([8.0, 16.0, 32.0])
+    return head
+
+
+@pytest.mark.parametrize("nc,conf,iou,bs,shapes", [
+    (80, 0.25, 0.45, 3, [(40, 40), (20, 20), (12, 12)]),     # C2-like thresholds, ragged 128-pixel tiles
+    (80, 0.001, 0.65, 2, [(40, 40), (20, 20), (12, 12)]),    # C3-like: nearly every row is a candidate
+    (1, 0.3, 0.3, 2, [(16, 24), (8, 12), (4, 6)]),           # C1-like single class
+])
+def test_fused_step_equals_two_call_path(nc, conf, iou, bs, shapes):
+    """yc_detect_fused == yc_head_forward + yc_nms_batched, bit for bit (rows, indices, counts)."""
+    from yolo_continuous_b200.pipeline import PostBackbone
+    ch = (64, 128, 256)
+    head = _bench_like_head(nc, ch, 3).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    xs = [torch.randn(bs, c, h, w, generator=g, device=DEV).to(torch.bfloat16) for c, (h, w) in zip(ch, shapes)]
+    res = []
+    for fused in (True, False):
+        pipe = PostBackbone(head, bs, shapes, torch.bfloat16, (320, 320), (240, 320), True, conf, iou, DEV,
+                            use_graph=False, fused=fused)
+        rows, idx, counts, offsets = pipe.run_device(xs)
+        assert pipe.fused == fused
+        tot = int(offsets[-1])
+        res.append((rows[:tot].clone(), idx[:tot].clone(), counts.clone(), offsets.clone()))
+    assert int(res[0][3][-1]) > 0
+    for a_, b_ in zip(res[0], res[1]):
+        assert torch.equal(a_, b_)
+    # and the host-buffer call with CUDA-graph replay returns the same detections
+    pipe = PostBackbone(head, bs, shapes, torch.bfloat16, (320, 320), (240, 320), True, conf, iou, DEV, use_graph=True)
+    for d_, s_ in zip(pipe.x_host, xs):
+        d_.copy_(s_)
+    for _ in range(2):
+        out = pipe.run_host()
+    off = res[0][3].cpu().numpy()
+    for b in range(bs):
+        want = res[0][0][off[b]:off[b + 1]].cpu().numpy()
+        assert (out[b] is None) == (len(want) == 0)
+        if out[b] is not None:
+            assert np.array_equal(out[b], want)
+
+
+def test_fused_step_vs_oracle_pipeline():
+    """Fused GPU step against the oracle pipeline on bf16-representable inputs, excluding candidates whose
+    score is within tolerance of the confidence threshold."""
+    from yolo_continuous_b200.pipeline import PostBackbone
+    ch, shapes, bs, nc, conf, iou = (64, 128, 256), [(16, 16), (8, 8), (4, 4)], 2, 80, 0.2, 0.45
+    head = _bench_like_head(nc, ch, 4)
+    g = torch.Generator().manual_seed(6)
+    xs = [torch.randn(bs, c, h, w, generator=g).to(torch.bfloat16) for c, (h, w) in zip(ch, shapes)]
+    p = _oracle_params(head, "idetect", True)
+    z_ref, _ = orc.head_forward("idetect", p, [x.float().numpy() for x in xs], [8.0, 16.0, 32.0])
+    z_ref = z_ref.copy()
+    z_ref[..., :4] /= np.float32(128.0)
+    sc = z_ref[..., 4] * z_ref[..., 5:].max(-1)
+    assert (np.abs(sc - conf) < 1e-4).sum() == 0, "pick another seed: a score sits on the threshold"
+    want, widx = orc.non_max_suppression(z_ref, nc, (128, 128), (96, 128), True, conf, iou, return_indices=True)
+    pipe = PostBackbone(head.to(DEV), bs, shapes, torch.bfloat16, (128, 128), (96, 128), True, conf, iou, DEV,
+                        use_graph=False)
+    rows, idx, counts, offsets = pipe.run_device([x.to(DEV) for x in xs])
+    assert pipe.fused
+    off = offsets.cpu().numpy()
+    assert sum(len(i) for i in widx) > 10
+    for b in range(bs):
+        assert np.array_equal(idx[off[b]:off[b + 1]].cpu().numpy(), widx[b])
+        got = rows[off[b]:off[b + 1]].cpu().numpy()
+        assert np.array_equal(got[:, 6], want[b][:, 6])
+        np.testing.assert_allclose(got[:, :6], want[b][:, :6], rtol=1e-3, atol=1e-2)

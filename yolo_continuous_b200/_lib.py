@@ -38,7 +38,7 @@ class NmsParams(C.Structure):
 
 EXPORTS = ["yc_last_error", "yc_version", "yc_device_check", "yc_head_pack_bytes", "yc_head_pack",
            "yc_head_forward", "yc_decode_box", "yc_nms_workspace_bytes", "yc_nms_batched",
-           "yc_nms_single", "yc_box_iou", "yc_cvt_bbox"]
+           "yc_nms_single", "yc_box_iou", "yc_cvt_bbox", "yc_detect_fused"]
 
 
 def _load():
@@ -61,6 +61,8 @@ def _load():
     lib.yc_nms_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.yc_nms_batched.argtypes = [C.c_void_p, C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.yc_detect_fused.argtypes = [C.POINTER(HeadDesc), C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_nms_single.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_box_iou.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "yc_common.cuh"
+#include "yc_nms.cuh"
 
 namespace yc {
 
@@ -28,7 +29,7 @@ int launch_head_generic(const yc_head_desc *d, int rows_total, const int *row_of
 // Runs the levels that fit the tcgen05 kernel and reports the others in *left_mask; returns
 // YC_ERR_UNSUPPORTED (reason in yc_last_error) when the head as a whole does not fit.
 int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, unsigned *left_mask,
-                        cudaStream_t stream);
+                        const FusedDetect *fused, cudaStream_t stream);
 
 // utils/bbox.py:62-72
 __global__ void box_iou_kernel(const float4 *__restrict__ b1, int n, const float4 *__restrict__ b2, int m,
@@ -86,9 +87,8 @@ extern "C" int yc_device_check(int dev)
     return YC_OK;
 }
 
-extern "C" int yc_head_forward(const yc_head_desc *d, yc_stream_t stream_)
+static int validate_head(const yc_head_desc *d, bool need_z, int *row_off, int *rows_total_out)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
     YC_REQUIRE(d, YC_ERR_INVALID, "yc_head_forward: null descriptor");
     YC_REQUIRE(d->nl >= 1 && d->nl <= YC_MAX_LEVELS && d->na >= 1 && d->na <= YC_MAX_ANCHORS && d->no >= 5 && d->bs >= 1,
                YC_ERR_INVALID, "yc_head_forward: bad nl=%d na=%d no=%d bs=%d", d->nl, d->na, d->no, d->bs);
@@ -96,12 +96,12 @@ extern "C" int yc_head_forward(const yc_head_desc *d, yc_stream_t stream_)
                d->kind);
     YC_REQUIRE(d->x_dtype == YC_F32 || d->x_dtype == YC_BF16, YC_ERR_INVALID, "yc_head_forward: bad x_dtype %d",
                d->x_dtype);
-    YC_REQUIRE(d->kind == YC_HEAD_RAW || d->z, YC_ERR_INVALID, "yc_head_forward: z is null");
+    YC_REQUIRE(d->kind == YC_HEAD_RAW || d->z || !need_z, YC_ERR_INVALID, "yc_head_forward: z is null");
     if (d->kind == YC_HEAD_IBIN) {
         YC_REQUIRE(d->bins && d->bin_count >= 1 && d->no > 2 * (d->bin_count + 1) + 3, YC_ERR_INVALID,
                    "yc_head_forward: IBin needs bins and no > 2*(bin_count+1)+3");
     }
-    int row_off[YC_MAX_LEVELS], rows_total = 0;
+    int rows_total = 0;
     for (int i = 0; i < d->nl; ++i) {
         const yc_head_level &lv = d->level[i];
         YC_REQUIRE(lv.x && lv.blob && lv.K > 0 && lv.H > 0 && lv.W > 0, YC_ERR_INVALID,
@@ -111,10 +111,20 @@ extern "C" int yc_head_forward(const yc_head_desc *d, yc_stream_t stream_)
         rows_total += d->na * lv.H * lv.W;
     }
     YC_REQUIRE((size_t)d->bs * rows_total < ((size_t)1 << 31), YC_ERR_UNSUPPORTED, "yc_head_forward: bs*rows >= 2^31");
+    *rows_total_out = rows_total;
+    return YC_OK;
+}
+
+extern "C" int yc_head_forward(const yc_head_desc *d, yc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int row_off[YC_MAX_LEVELS], rows_total = 0;
+    const int vrc = validate_head(d, true, row_off, &rows_total);
+    if (vrc != YC_OK) return vrc;
     const unsigned all = (1u << d->nl) - 1u;
     if (d->path == YC_PATH_GENERIC) return launch_head_generic(d, rows_total, row_off, all, stream);
     unsigned left = all;
-    const int rc = launch_head_tcgen05(d, rows_total, row_off, &left, stream);
+    const int rc = launch_head_tcgen05(d, rows_total, row_off, &left, nullptr, stream);
     if (rc == YC_ERR_UNSUPPORTED && d->path == YC_PATH_AUTO) return launch_head_generic(d, rows_total, row_off, all, stream);
     if (rc != YC_OK) return rc;
     if (left) {
@@ -146,4 +156,34 @@ extern "C" int yc_cvt_bbox(const float *in, int n, int flag, float *out, yc_stre
     cvt_bbox_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4 *)in, n, flag, (float4 *)out);
     YC_CUDA(cudaGetLastError());
     return YC_OK;
+}
+
+extern "C" int yc_detect_fused(const yc_head_desc *d, const yc_nms_params *p, void *workspace, size_t workspace_bytes,
+                               float *out_rows, int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets,
+                               yc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int row_off[YC_MAX_LEVELS], rows_total = 0;
+    const int vrc = validate_head(d, false, row_off, &rows_total);
+    if (vrc != YC_OK) return vrc;
+    YC_REQUIRE(p && workspace && out_rows && out_idx && out_counts && out_offsets, YC_ERR_INVALID,
+               "yc_detect_fused: null argument");
+    YC_REQUIRE(d->kind == YC_HEAD_IDETECT, YC_ERR_UNSUPPORTED, "yc_detect_fused: IDetect-style decode only");
+    YC_REQUIRE(p->bs == d->bs && p->rows == rows_total && p->nc == d->no - 5 && p->nc > 0, YC_ERR_INVALID,
+               "yc_detect_fused: nms params (bs=%d rows=%d nc=%d) do not match the head (bs=%d rows=%d no=%d)", p->bs,
+               p->rows, p->nc, d->bs, rows_total, d->no);
+    YC_REQUIRE(!p->correct_boxes || p->image_hw, YC_ERR_INVALID, "yc_detect_fused: correct_boxes needs image_hw");
+    YC_REQUIRE(p->bs <= 65535, YC_ERR_UNSUPPORTED, "yc_detect_fused: bs > 65535");
+    void *base = (void *)round_up_sz((size_t)workspace, 256);
+    FusedDetect f;
+    f.ws = carve(base, p->bs, p->rows, p->nc);
+    YC_REQUIRE(f.ws.total_bytes + ((char *)base - (char *)workspace) <= workspace_bytes, YC_ERR_WORKSPACE,
+               "yc_detect_fused: workspace %zu < %zu", workspace_bytes, f.ws.total_bytes + 256);
+    f.conf = p->conf_thres; f.div_w = p->box_div_w; f.div_h = p->box_div_h; f.nc = p->nc;
+    YC_CUDA(cudaMemsetAsync(f.ws.counters, 0, f.ws.counters_bytes, stream));
+    unsigned left = 0;
+    const int rc = launch_head_tcgen05(d, rows_total, row_off, &left, &f, stream);
+    if (rc != YC_OK) return rc;
+    YC_REQUIRE(left == 0, YC_ERR_UNSUPPORTED, "yc_detect_fused: levels 0x%x do not fit the tcgen05 kernel: %s", left, g_err);
+    return launch_nms_tail(p, f.ws, out_rows, out_idx, out_counts, out_offsets, stream);
 }

@@ -17,6 +17,7 @@
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
 // round-robin tile scheduler over all (level, image, 128-pixel block) tiles, heaviest level first.
 #include "yc_common.cuh"
+#include "yc_nms.cuh"
 #include "yc_sm100.cuh"
 
 namespace yc {
@@ -25,7 +26,7 @@ using namespace sm100;
 
 constexpr int TC_BM = 128;       // pixels per tile (UMMA M)
 constexpr int TC_BK = 32;        // k per pipeline stage
-constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_STAGES = 8;   // 4 when the z slabs occupy shared memory, 8 in the fused mode
 constexpr int TC_MAX_N = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 8 KB: two {64 px, 32 k} bf16 boxes
 constexpr int TC_B_BYTES_MAX = TC_MAX_N * TC_BK * 2; // 16 KB
@@ -54,7 +55,13 @@ struct TcParams {
     float *z;
     uint32_t idesc;
     uint32_t b_bytes;          // npad * TC_BK * 2
-    uint32_t slab_bytes;       // 32 * no * 4, rounded up to 16
+    uint32_t slab_bytes;       // 32 * no * 4, rounded up to 16 (0 in the fused mode)
+    int stages;                // depth of the smem ring
+    // fused mode (yc_detect_fused): the epilogue thresholds and emits NMS candidates, z is never written
+    int fused;
+    int nc;
+    float conf, div_w, div_h;
+    NmsWs ws;
 };
 
 struct TcMaps {
@@ -120,6 +127,36 @@ __device__ __forceinline__ void epi_row(uint32_t taddr, int no, const float2 *__
     if (rem & 1) { epi_chunk<1, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); }
 }
 
+
+// ---- fused epilogue (S3): class max / threshold / candidate emission straight from TMEM -----------------
+// logits of W consecutive class columns starting at accumulator column c (class index c - 5)
+template <int W, bool EXACT>
+__device__ __forceinline__ void cls_chunk(uint32_t taddr, int c, const float2 *__restrict__ sb, float &bestv, int &besti)
+{
+    uint32_t v[W];
+    TmemLd<W>::ld(taddr + (uint32_t)c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const float2 s_b = __ldg(sb + c + j);
+        float t = fmaf(__uint_as_float(v[j]), s_b.x, s_b.y);
+        if (EXACT) t = sigmoidf_fast(t); // compare what z would hold (first maximum of the sigmoids, torch.max)
+        if (t > bestv) { bestv = t; besti = c + j - 5; }
+    }
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void cls_scan(uint32_t taddr, int no, const float2 *__restrict__ sb, float &bestv, int &besti)
+{
+    int c = 5;
+    for (; c + 16 <= no; c += 16) cls_chunk<16, EXACT>(taddr, c, sb, bestv, besti);
+    const int rem = no - c;
+    if (rem & 8) { cls_chunk<8, EXACT>(taddr, c, sb, bestv, besti); c += 8; }
+    if (rem & 4) { cls_chunk<4, EXACT>(taddr, c, sb, bestv, besti); c += 4; }
+    if (rem & 2) { cls_chunk<2, EXACT>(taddr, c, sb, bestv, besti); c += 2; }
+    if (rem & 1) { cls_chunk<1, EXACT>(taddr, c, sb, bestv, besti); }
+}
+
 // warp-cooperative write of `nv` finished rows from the slab to global memory
 __device__ __forceinline__ void slab_store(float *__restrict__ gdst, const float *__restrict__ slab, int nv, int no, int lane)
 {
@@ -143,14 +180,15 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // carve: [stages: A|B] (1024-aligned) [slabs] [barriers]
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *stage_base = smem;
-    float *slabs = (float *)(smem + TC_STAGES * TC_STAGE_BYTES);
+    const int n_stages = P.stages;
+    float *slabs = (float *)(smem + n_stages * TC_STAGE_BYTES);
     const int n_epi_warps = 4 * P.na;
     uint64_t *bars = (uint64_t *)((uint8_t *)slabs + (size_t)n_epi_warps * P.slab_bytes);
-    uint64_t *full_bar = bars;                    // [TC_STAGES]
-    uint64_t *empty_bar = bars + TC_STAGES;       // [TC_STAGES]
-    uint64_t *tfull_bar = bars + 2 * TC_STAGES;   // [2]
-    uint64_t *tempty_bar = bars + 2 * TC_STAGES + 2; // [2]
-    uint32_t *tmem_ptr_smem = (uint32_t *)(bars + 2 * TC_STAGES + 4);
+    uint64_t *full_bar = bars;                        // [TC_MAX_STAGES]
+    uint64_t *empty_bar = bars + TC_MAX_STAGES;       // [TC_MAX_STAGES]
+    uint64_t *tfull_bar = bars + 2 * TC_MAX_STAGES;   // [2]
+    uint64_t *tempty_bar = bars + 2 * TC_MAX_STAGES + 2; // [2]
+    uint32_t *tmem_ptr_smem = (uint32_t *)(bars + 2 * TC_MAX_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -161,7 +199,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < TC_STAGES; ++i) {
+        for (int i = 0; i < n_stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
@@ -192,7 +230,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     tma_load_3d(sa, &maps.a[tc.lv], &full_bar[stage], tc.p0, kb * TC_BK, tc.b);
                     tma_load_3d(sa + TC_A_BYTES / 2, &maps.a[tc.lv], &full_bar[stage], tc.p0 + 64, kb * TC_BK, tc.b);
                     tma_load_2d(sb, &maps.b[tc.lv], &full_bar[stage], kb * TC_BK, 0);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -224,7 +262,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     }
                     mma_commit(&empty_bar[stage]); // frees the smem slot when these MMAs retire
                     if (kb == nkb - 1) mma_commit(&tfull_bar[buf]);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -251,6 +289,47 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
             mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
+            if (P.fused) {
+                // box + objectness logits (columns 0..4), then the running maximum of the class logits
+                uint32_t v4[4], v1[1];
+                TmemLd<4>::ld(taddr, v4);
+                TmemLd<1>::ld(taddr + 4u, v1);
+                tmem_ld_wait();
+                float tb[5];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 s_b = __ldg(sb + j);
+                    tb[j] = fmaf(__uint_as_float(v4[j]), s_b.x, s_b.y);
+                }
+                {
+                    const float2 s_b = __ldg(sb + 4);
+                    tb[4] = fmaf(__uint_as_float(v1[0]), s_b.x, s_b.y);
+                }
+                float bestv = -INFINITY;
+                int besti = 0;
+                cls_scan<false>(taddr, no, sb, bestv, besti);
+                const float obj = sigmoidf_fast(tb[4]);
+                bool pass = lane < nv && __fmul_rn(obj, sigmoidf_fast(bestv)) >= P.conf;
+                if (__any_sync(0xffffffffu, pass)) {
+                    // rare: redo the class scan on the sigmoid values so that ties resolve exactly as on z
+                    float bv = -1.0f;
+                    int best = 0;
+                    cls_scan<true>(taddr, no, sb, bv, best);
+                    const float score = __fmul_rn(obj, bv);
+                    pass = pass && score >= P.conf;
+                    const float cx = decode_xy(sigmoidf_fast(tb[0]), gx, L.stride);
+                    const float cy = decode_xy(sigmoidf_fast(tb[1]), gy, L.stride);
+                    const float bw = decode_wh(sigmoidf_fast(tb[2]), aw), bh = decode_wh(sigmoidf_fast(tb[3]), ah);
+                    float x1, y1, x2, y2;
+                    xywh_to_corners(cx, cy, bw, bh, P.div_w, P.div_h, x1, y1, x2, y2);
+                    emit_candidates(pass, tc.b, L.row_off + a * L.HW + p, P.rows_total, P.nc, x1, y1, x2, y2, obj, bv,
+                                    score, best, P.ws);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                continue;
+            }
             if (L.raw) {
                 if (lane == 0) bulk_wait_read0(); // previous store from this slab has been read out
                 __syncwarp();
@@ -281,6 +360,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -301,7 +381,7 @@ static EncodeTiledFn encode_tiled()
 static int g_num_sms = 0;
 
 int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, unsigned *left_mask,
-                        cudaStream_t stream)
+                        const FusedDetect *fused, cudaStream_t stream)
 {
     const int N = d->na * d->no, npad = round_up(N, 16);
     YC_REQUIRE(d->x_dtype == YC_BF16, YC_ERR_UNSUPPORTED, "tcgen05 head: feature maps must be bf16 (fp32 maps use the exact FFMA path)");
@@ -312,8 +392,10 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     EncodeTiledFn enc = encode_tiled();
     YC_REQUIRE(enc != nullptr, YC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
 
-    const uint32_t slab_bytes = (uint32_t)round_up(32 * d->no * 4, 16);
-    const size_t smem_bytes = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)4 * d->na * slab_bytes + 256;
+    const uint32_t slab_bytes = fused ? 0u : (uint32_t)round_up(32 * d->no * 4, 16);
+    int stages = TC_MAX_STAGES;
+    while (stages > 2 && 1024 + (size_t)stages * TC_STAGE_BYTES + (size_t)4 * d->na * slab_bytes + 256 > 227 * 1024) --stages;
+    const size_t smem_bytes = 1024 + (size_t)stages * TC_STAGE_BYTES + (size_t)4 * d->na * slab_bytes + 256;
     YC_REQUIRE(smem_bytes <= 227 * 1024, YC_ERR_UNSUPPORTED, "tcgen05 head: needs %zu bytes of shared memory", smem_bytes);
 
     // which levels fit: TMA needs 16-byte aligned bases and row pitches
@@ -322,7 +404,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         const yc_head_level &lv = d->level[i];
         const size_t HW = (size_t)lv.H * lv.W;
         const bool ok = (HW * 2) % 16 == 0 && ((size_t)lv.K * 2) % 16 == 0 && ((uintptr_t)lv.x & 15) == 0 &&
-                        (d->kind != YC_HEAD_RAW || lv.raw);
+                        (d->kind != YC_HEAD_RAW || lv.raw) && !(fused && lv.raw);
         if (ok) fit |= 1u << i;
         else set_error("level %d (K=%d, H*W=%zu) does not meet the TMA alignment rules", i, lv.K, HW);
     }
@@ -348,6 +430,12 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     P.idesc = instr_desc_f16(/*bf16*/ 1, /*A MN-major*/ 1, /*B K-major*/ 0, TC_BM, (uint32_t)npad);
     P.b_bytes = (uint32_t)npad * TC_BK * 2;
     P.slab_bytes = slab_bytes;
+    P.stages = stages;
+    if (fused) {
+        P.fused = 1; P.nc = fused->nc; P.conf = fused->conf; P.div_w = fused->div_w; P.div_h = fused->div_h;
+        P.ws = fused->ws;
+        P.write_z = 0;
+    }
     int tiles = 0;
     for (int s = 0; s < n; ++s) {
         const int i = order[s];

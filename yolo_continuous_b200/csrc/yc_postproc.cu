@@ -4,6 +4,7 @@
 // no host round trip.  All comparisons that decide membership are evaluated exactly as the
 // reference evaluates them (binary32, round-to-nearest, no FMA contraction).
 #include "yc_common.cuh"
+#include "yc_nms.cuh"
 
 namespace yc {
 
@@ -11,61 +12,6 @@ constexpr int TC_ROWS = 128;    // rows per CTA in the threshold/compaction kern
 constexpr int NMS_NT = 128;     // threads per NMS CTA == sorted boxes per chunk
 constexpr int SORT_SMEM = 2048; // segments up to this size are sorted in shared memory
 constexpr int KEPT_SMEM = 512;  // kept boxes cached in shared memory per segment
-
-struct NmsWs {
-    float4 *box;                    // [bs*rows] corners, indexed by original row
-    float2 *oc;                     // [bs*rows] (obj, class_conf)
-    unsigned long long *key_unsorted; // [bs*rows] candidates in arrival order, per image
-    int *cls_unsorted;              // [bs*rows]
-    unsigned long long *key_bucket; // [bs*rows] candidates grouped by class, then sorted in place
-    int *kept_row;                  // [bs*rows] kept original rows, per segment
-    float4 *kept_box;               // [bs*rows] spill of kept boxes beyond KEPT_SMEM
-    int *counters;                  // start of the zero-initialised region
-    int *cand_count;                // [bs]
-    int *hist;                      // [bs*nc] candidates per (image, class)
-    int *cursor;                    // [bs*nc]
-    int *kept_count;                // [bs*nc]
-    int *seg_off;                   // [bs*nc]
-    int *kept_off;                  // [bs*nc]
-    size_t counters_bytes;
-    size_t total_bytes;
-};
-
-static NmsWs carve(void *base, int bs, int rows, int nc)
-{
-    NmsWs w;
-    char *p = (char *)base;
-    const size_t n = (size_t)bs * rows, s = (size_t)bs * nc;
-    auto take = [&](size_t bytes) { char *q = p; p += round_up_sz(bytes, 256); return q; };
-    w.box = (float4 *)take(n * sizeof(float4));
-    w.kept_box = (float4 *)take(n * sizeof(float4));
-    w.key_unsorted = (unsigned long long *)take(n * 8);
-    w.key_bucket = (unsigned long long *)take(n * 8);
-    w.oc = (float2 *)take(n * sizeof(float2));
-    w.cls_unsorted = (int *)take(n * 4);
-    w.kept_row = (int *)take(n * 4);
-    char *c0 = p;
-    w.cand_count = (int *)take((size_t)bs * 4);
-    w.hist = (int *)take(s * 4);
-    w.cursor = (int *)take(s * 4);
-    w.kept_count = (int *)take(s * 4);
-    w.counters = (int *)c0;
-    w.counters_bytes = (size_t)(p - c0);
-    w.seg_off = (int *)take(s * 4);
-    w.kept_off = (int *)take(s * 4);
-    w.total_bytes = (size_t)(p - (char *)base);
-    return w;
-}
-
-// score -> 64-bit key whose ascending order is (score descending, original row ascending),
-// i.e. the order of a stable descending sort (torchvision nms; detect.py:133).
-__device__ __forceinline__ unsigned long long make_key(float score, int row)
-{
-    unsigned int u = __float_as_uint(score);
-    if (score == 0.0f) u = 0u; // -0 == +0 for the reference's sort
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    return ((unsigned long long)(~u) << 32) | (unsigned int)row;
-}
 
 // ---- mbarrier / bulk-copy helpers (TMA 1D) -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,12 +79,7 @@ __global__ void __launch_bounds__(TC_ROWS) threshold_compact_kernel(float *__res
     float x1 = 0, y1 = 0, x2 = 0, y2 = 0, obj = 0, bv = 0, score = 0;
     if (tid < m) {
         const float *q = tile + tid * row_stride;
-        float cx = q[0], cy = q[1], bw = q[2], bh = q[3];
-        if (div_w > 0.f) { cx = __fdiv_rn(cx, div_w); bw = __fdiv_rn(bw, div_w); }
-        if (div_h > 0.f) { cy = __fdiv_rn(cy, div_h); bh = __fdiv_rn(bh, div_h); }
-        const float hw = __fmul_rn(bw, 0.5f), hh = __fmul_rn(bh, 0.5f);
-        x1 = __fsub_rn(cx, hw); y1 = __fsub_rn(cy, hh);
-        x2 = __fadd_rn(cx, hw); y2 = __fadd_rn(cy, hh);
+        xywh_to_corners(q[0], q[1], q[2], q[3], div_w, div_h, x1, y1, x2, y2);
         obj = q[4];
         bv = q[5];
 #pragma unroll 8
@@ -153,22 +94,7 @@ __global__ void __launch_bounds__(TC_ROWS) threshold_compact_kernel(float *__res
             o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
         }
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-    if (ballot) {
-        const int lane = tid & 31, leader = __ffs(ballot) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&ws.cand_count[b], __popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (pass) {
-            const size_t ib = (size_t)b * rows;
-            const int slot = base + __popc(ballot & ((1u << lane) - 1u));
-            ws.box[ib + r] = make_float4(x1, y1, x2, y2);
-            ws.oc[ib + r] = make_float2(obj, bv);
-            ws.key_unsorted[ib + slot] = make_key(score, r);
-            ws.cls_unsorted[ib + slot] = best;
-            atomicAdd(&ws.hist[(size_t)b * nc + best], 1);
-        }
-    }
+    emit_candidates(pass, b, r, rows, nc, x1, y1, x2, y2, obj, bv, score, best, ws);
 }
 
 // ---- K2: per-image exclusive scan of the class histogram ----------------------------------------
@@ -484,6 +410,20 @@ static float thr_to_f32_floor(double thr)
     return tf;
 }
 
+int launch_nms_tail(const yc_nms_params *p, const NmsWs &ws, float *out_rows, int *out_idx, int *out_counts,
+                    int *out_offsets, cudaStream_t stream)
+{
+    segment_offsets_kernel<<<p->bs, 256, 0, stream>>>(p->nc, ws);
+    bucket_scatter_kernel<<<dim3((p->rows + 255) / 256, p->bs), 256, 0, stream>>>(p->rows, p->nc, ws);
+    nms_segment_kernel<<<dim3(p->nc, p->bs), NMS_NT, 0, stream>>>(p->rows, p->nc, thr_to_f32_floor(p->nms_thres), ws);
+    kept_scan_kernel<<<1, 1024, 0, stream>>>(p->bs, p->nc, ws, out_counts, out_offsets);
+    CorrectParams cp{p->correct_boxes, p->letterbox, p->input_h, p->input_w, (const int *)p->image_hw, p->image_hw_stride};
+    gather_kernel<<<dim3((p->nc + 3) / 4, p->bs), 128, 0, stream>>>(p->rows, p->nc, ws, out_offsets, out_rows, out_idx,
+                                                                    cp);
+    YC_CUDA(cudaGetLastError());
+    return YC_OK;
+}
+
 } // namespace yc
 
 using namespace yc;
@@ -520,15 +460,7 @@ extern "C" int yc_nms_batched(float *pred, const yc_nms_params *p, void *workspa
     dim3 g1((p->rows + TC_ROWS - 1) / TC_ROWS, p->bs);
     threshold_compact_kernel<<<g1, TC_ROWS, tile_bytes, stream>>>(pred, p->rows, p->row_stride, p->nc, p->conf_thres,
                                                                   p->write_corners, p->box_div_w, p->box_div_h, ws);
-    segment_offsets_kernel<<<p->bs, 256, 0, stream>>>(p->nc, ws);
-    bucket_scatter_kernel<<<dim3((p->rows + 255) / 256, p->bs), 256, 0, stream>>>(p->rows, p->nc, ws);
-    nms_segment_kernel<<<dim3(p->nc, p->bs), NMS_NT, 0, stream>>>(p->rows, p->nc, thr_to_f32_floor(p->nms_thres), ws);
-    kept_scan_kernel<<<1, 1024, 0, stream>>>(p->bs, p->nc, ws, out_counts, out_offsets);
-    CorrectParams cp{p->correct_boxes, p->letterbox, p->input_h, p->input_w, p->image_hw, p->image_hw_stride};
-    gather_kernel<<<dim3((p->nc + 3) / 4, p->bs), 128, 0, stream>>>(p->rows, p->nc, ws, out_offsets, out_rows, out_idx,
-                                                                    cp);
-    YC_CUDA(cudaGetLastError());
-    return YC_OK;
+    return launch_nms_tail(p, ws, out_rows, out_idx, out_counts, out_offsets, stream);
 }
 
 extern "C" int yc_nms_single(const float *boxes, const float *scores, int n, double thr, void *workspace,

@@ -20,7 +20,7 @@ from . import _lib
 class PostBackbone:
     def __init__(self, head, bs, shapes, dtype=torch.bfloat16, input_shape=(640, 640), image_shape=(640, 640),
                  letterbox_image=True, conf_thres=0.25, nms_thres=0.45, device="cuda:0", use_graph=True,
-                 spec_rows=65536):
+                 spec_rows=65536, fused=True):
         self.head, self.bs, self.shapes = head, bs, [tuple(s) for s in shapes]
         self.device = torch.device(device)
         self.dtype = dtype
@@ -71,7 +71,10 @@ class PostBackbone:
         p.image_hw, p.image_hw_stride = self.image_hw.data_ptr(), (2 if hw.shape[0] > 1 else 0)
         p.box_div_w, p.box_div_h = float(input_shape[1]), float(input_shape[0])
         self.nms_params = p
-        self.kernels_per_step = 1 + 6   # head_tc_kernel + 6 post-processing kernels (memset is not a kernel)
+        # fused mode: one head kernel whose epilogue emits the NMS candidates (z never written) + 5 NMS kernels;
+        # otherwise head kernel (writes z) + threshold/compaction + the same 5.  (memsets are not kernels)
+        self.fused = fused and dtype == torch.bfloat16
+        self.kernels_per_step = 6 if self.fused else 7
         self.graph = None
         self.use_graph = use_graph
         self._graph_ptrs = None
@@ -83,8 +86,16 @@ class PostBackbone:
                 raise _lib.YcError(f"level {i}: expected contiguous {tuple(self.x_dev[i].shape)} {self.dtype}")
             self.desc.level[i].x = x.data_ptr()
         s = _lib.stream_ptr(self.device)
-        _lib.check(_lib.lib.yc_head_forward(C.byref(self.desc), s), "yc_head_forward")
         m = self.meta.data_ptr()
+        if self.fused:
+            rc = _lib.lib.yc_detect_fused(C.byref(self.desc), C.byref(self.nms_params), self.ws.data_ptr(),
+                                          self.ws.numel(), self.out_rows.data_ptr(), self.out_idx.data_ptr(),
+                                          m, m + 4 * self.bs, s)
+            if rc != _lib.YC_ERR_UNSUPPORTED:
+                _lib.check(rc, "yc_detect_fused")
+                return
+            self.fused, self.kernels_per_step = False, 7   # shape does not fit the tcgen05 kernel: two-call path
+        _lib.check(_lib.lib.yc_head_forward(C.byref(self.desc), s), "yc_head_forward")
         _lib.check(_lib.lib.yc_nms_batched(self.z.data_ptr(), C.byref(self.nms_params), self.ws.data_ptr(),
                                            self.ws.numel(), self.out_rows.data_ptr(), self.out_idx.data_ptr(),
                                            m, m + 4 * self.bs, s), "yc_nms_batched")
