@@ -32,6 +32,7 @@ NC = 80
 CONF, IOU = 0.25, 0.45
 INPUT_SHAPE, IMAGE_SHAPE = (640, 640), (512, 773)
 BYTES_PER_IMG = {"bf16": 2867200 * 2 + 25200 * 85 * 4, "fp32": 2867200 * 4 + 25200 * 85 * 4}  # S1: maps in + z out
+BYTES_PER_IMG_FUSED = {"bf16": 2867200 * 2, "fp32": 2867200 * 4}                              # S3: maps in (+28 B/candidate)
 FLOPS_PER_IMG = 2 * 255 * 2867200
 
 
@@ -152,6 +153,7 @@ def main():
     ap.add_argument("--bs", type=int, default=64)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="materialise z (drop-in forward) and run the stand-alone threshold kernel")
     ap.add_argument("--profile", action="store_true", help="device-resident loop only (for ncu runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +181,8 @@ def main():
     K = args.steps
     tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     head = make_head().to(dev)
-    pipe = PostBackbone(head, args.bs, SHAPES, tdt, INPUT_SHAPE, IMAGE_SHAPE, True, CONF, IOU, dev, use_graph=False)
+    pipe = PostBackbone(head, args.bs, SHAPES, tdt, INPUT_SHAPE, IMAGE_SHAPE, True, CONF, IOU, dev, use_graph=False,
+                        fused=not args.unfused)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     xs = [torch.randn(args.bs, c, h, w, generator=g, device=dev).to(tdt) for c, (h, w) in zip(CH, SHAPES)]
     for d_, h_ in zip(xs, pipe.x_host):
@@ -207,17 +210,25 @@ def main():
     sync_all()
     t0.record()
     for i in range(K):
-        # same launches as pipe.run_device, with the head kernel bracketed on its own stream
+        # same launches as pipe.run_device, with the head kernel bracketed by events on its own stream
         for j, x in enumerate(xs):
             pipe.desc.level[j].x = x.data_ptr()
         s = _lib.stream_ptr(dev)
-        ev[i][0].record()
-        _lib.check(_lib.lib.yc_head_forward(pipe.desc, s), "yc_head_forward")
-        ev[i][1].record()
         m = pipe.meta.data_ptr()
-        _lib.check(_lib.lib.yc_nms_batched(pipe.z.data_ptr(), pipe.nms_params, pipe.ws.data_ptr(), pipe.ws.numel(),
-                                           pipe.out_rows.data_ptr(), pipe.out_idx.data_ptr(), m, m + 4 * args.bs, s),
-                   "yc_nms_batched")
+        ev[i][0].record()
+        if pipe.fused:
+            _lib.check(_lib.lib.yc_detect_fused_head(pipe.desc, pipe.nms_params, pipe.ws.data_ptr(), pipe.ws.numel(), s),
+                       "yc_detect_fused_head")
+            ev[i][1].record()
+            _lib.check(_lib.lib.yc_nms_from_candidates(pipe.nms_params, pipe.ws.data_ptr(), pipe.ws.numel(),
+                                                       pipe.out_rows.data_ptr(), pipe.out_idx.data_ptr(), m,
+                                                       m + 4 * args.bs, s), "yc_nms_from_candidates")
+        else:
+            _lib.check(_lib.lib.yc_head_forward(pipe.desc, s), "yc_head_forward")
+            ev[i][1].record()
+            _lib.check(_lib.lib.yc_nms_batched(pipe.z.data_ptr(), pipe.nms_params, pipe.ws.data_ptr(), pipe.ws.numel(),
+                                               pipe.out_rows.data_ptr(), pipe.out_idx.data_ptr(), m, m + 4 * args.bs, s),
+                       "yc_nms_batched")
         if world > 1:
             gather_detections(pipe.out_rows, pipe.meta[:args.bs])
     t1.record()
@@ -284,13 +295,27 @@ def main():
     except (OSError, ValueError):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    bytes_launch = BYTES_PER_IMG[args.dtype] * args.bs
+    bytes_launch = (BYTES_PER_IMG_FUSED if pipe.fused else BYTES_PER_IMG)[args.dtype] * args.bs
     achieved = bytes_launch / (head_ms / 1e3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"head_{args.dtype}_bs{args.bs}")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"head_{'fused_' if pipe.fused else ''}{args.dtype}_bs{args.bs}")
     except (OSError, ValueError):
         pass
+    tflops = FLOPS_PER_IMG * args.bs / (head_ms / 1e3) / 1e12
+    roofline = {"kernel": "head_tc_kernel" if args.dtype == "bf16" else "head_generic_kernel",
+                "stage": "S3 fused head->candidates (z never written)" if pipe.fused else "S1 head->z",
+                "peak_source": peak_src, "traffic": traffic, "kernel_ms": head_ms,
+                "kernel_share_of_step": head_ms / (ms / K), "bytes_per_launch": bytes_launch,
+                "flops_per_launch": FLOPS_PER_IMG * args.bs}
+    if pipe.fused:
+        # S3 moves 5.73 MB/img but still needs 1.462 GFLOP/img: the tensor pipe binds first
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        roofline.update({"bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
+                         "hbm_gbs": achieved, "hbm_frac": achieved / hbm_peak})
+    else:
+        roofline.update({"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "tensor_tflops": tflops})
     line = {
         "metric": "post_backbone_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -300,11 +325,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
                 "d2h_bytes_per_step": pipe.d2h_bytes(total_rows), "ms_per_step": e_ms / K},
         "gpu_launches": K * pipe.kernels_per_step,
-        "roofline": {"kernel": "head_tc_kernel" if args.dtype == "bf16" else "head_generic_kernel", "bound": "hbm",
-                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_launch,
-                     "kernel_ms": head_ms, "kernel_share_of_step": head_ms / (ms / K),
-                     "tensor_tflops": FLOPS_PER_IMG * args.bs / (head_ms / 1e3) / 1e12},
+        "roofline": roofline,
         "detections_per_step": n_det, "nms_p50_ms_per_image_bs1": nms_p50,
     }
     if world == 1 and not args.no_cpu_baseline:

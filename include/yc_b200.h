@@ -139,6 +139,14 @@ YC_API int yc_nms_batched(float *pred, const yc_nms_params *p, void *workspace, 
 YC_API int yc_detect_fused(const yc_head_desc *desc, const yc_nms_params *p, void *workspace, size_t workspace_bytes,
                     float *out_rows, int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets, yc_stream_t stream);
 
+/* The two halves of yc_detect_fused, for callers that want to time or overlap them separately:
+ * yc_detect_fused_head clears the counters and runs the head kernel, which leaves the candidates of every image
+ * in `workspace`; yc_nms_from_candidates runs the per-class NMS + gather on them. */
+YC_API int yc_detect_fused_head(const yc_head_desc *desc, const yc_nms_params *p, void *workspace, size_t workspace_bytes,
+                         yc_stream_t stream);
+YC_API int yc_nms_from_candidates(const yc_nms_params *p, void *workspace, size_t workspace_bytes, float *out_rows,
+                           int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets, yc_stream_t stream);
+
 /* torchvision.ops.nms drop-in for one box set (detect.py:133): boxes [n,4] xyxy, scores [n].
  * keep [n] receives kept indices in score order, *keep_count_dev their number. workspace from
  * yc_nms_workspace_bytes(1, n, 1). */

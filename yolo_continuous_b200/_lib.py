@@ -38,7 +38,8 @@ class NmsParams(C.Structure):
 
 EXPORTS = ["yc_last_error", "yc_version", "yc_device_check", "yc_head_pack_bytes", "yc_head_pack",
            "yc_head_forward", "yc_decode_box", "yc_nms_workspace_bytes", "yc_nms_batched",
-           "yc_nms_single", "yc_box_iou", "yc_cvt_bbox", "yc_detect_fused"]
+           "yc_nms_single", "yc_box_iou", "yc_cvt_bbox", "yc_detect_fused",
+           "yc_detect_fused_head", "yc_nms_from_candidates"]
 
 
 def _load():
@@ -63,6 +64,9 @@ def _load():
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_detect_fused.argtypes = [C.POINTER(HeadDesc), C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.yc_detect_fused_head.argtypes = [C.POINTER(HeadDesc), C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.yc_nms_from_candidates.argtypes = [C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_nms_single.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_box_iou.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

@@ -158,32 +158,63 @@ extern "C" int yc_cvt_bbox(const float *in, int n, int flag, float *out, yc_stre
     return YC_OK;
 }
 
-extern "C" int yc_detect_fused(const yc_head_desc *d, const yc_nms_params *p, void *workspace, size_t workspace_bytes,
-                               float *out_rows, int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets,
-                               yc_stream_t stream_)
+static int fused_setup(const yc_head_desc *d, const yc_nms_params *p, void *workspace, size_t workspace_bytes,
+                       int *row_off, int *rows_total, FusedDetect *f)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    int row_off[YC_MAX_LEVELS], rows_total = 0;
-    const int vrc = validate_head(d, false, row_off, &rows_total);
+    const int vrc = validate_head(d, false, row_off, rows_total);
     if (vrc != YC_OK) return vrc;
-    YC_REQUIRE(p && workspace && out_rows && out_idx && out_counts && out_offsets, YC_ERR_INVALID,
-               "yc_detect_fused: null argument");
+    YC_REQUIRE(p && workspace, YC_ERR_INVALID, "yc_detect_fused: null argument");
     YC_REQUIRE(d->kind == YC_HEAD_IDETECT, YC_ERR_UNSUPPORTED, "yc_detect_fused: IDetect-style decode only");
-    YC_REQUIRE(p->bs == d->bs && p->rows == rows_total && p->nc == d->no - 5 && p->nc > 0, YC_ERR_INVALID,
+    YC_REQUIRE(p->bs == d->bs && p->rows == *rows_total && p->nc == d->no - 5 && p->nc > 0, YC_ERR_INVALID,
                "yc_detect_fused: nms params (bs=%d rows=%d nc=%d) do not match the head (bs=%d rows=%d no=%d)", p->bs,
-               p->rows, p->nc, d->bs, rows_total, d->no);
+               p->rows, p->nc, d->bs, *rows_total, d->no);
     YC_REQUIRE(!p->correct_boxes || p->image_hw, YC_ERR_INVALID, "yc_detect_fused: correct_boxes needs image_hw");
     YC_REQUIRE(p->bs <= 65535, YC_ERR_UNSUPPORTED, "yc_detect_fused: bs > 65535");
     void *base = (void *)round_up_sz((size_t)workspace, 256);
+    f->ws = carve(base, p->bs, p->rows, p->nc);
+    YC_REQUIRE(f->ws.total_bytes + ((char *)base - (char *)workspace) <= workspace_bytes, YC_ERR_WORKSPACE,
+               "yc_detect_fused: workspace %zu < %zu", workspace_bytes, f->ws.total_bytes + 256);
+    f->conf = p->conf_thres; f->div_w = p->box_div_w; f->div_h = p->box_div_h; f->nc = p->nc;
+    return YC_OK;
+}
+
+extern "C" int yc_detect_fused_head(const yc_head_desc *d, const yc_nms_params *p, void *workspace,
+                                    size_t workspace_bytes, yc_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int row_off[YC_MAX_LEVELS], rows_total = 0;
     FusedDetect f;
-    f.ws = carve(base, p->bs, p->rows, p->nc);
-    YC_REQUIRE(f.ws.total_bytes + ((char *)base - (char *)workspace) <= workspace_bytes, YC_ERR_WORKSPACE,
-               "yc_detect_fused: workspace %zu < %zu", workspace_bytes, f.ws.total_bytes + 256);
-    f.conf = p->conf_thres; f.div_w = p->box_div_w; f.div_h = p->box_div_h; f.nc = p->nc;
+    const int src = fused_setup(d, p, workspace, workspace_bytes, row_off, &rows_total, &f);
+    if (src != YC_OK) return src;
+    // check the shape before touching the workspace, so that an unsupported call has no side effects
     YC_CUDA(cudaMemsetAsync(f.ws.counters, 0, f.ws.counters_bytes, stream));
     unsigned left = 0;
     const int rc = launch_head_tcgen05(d, rows_total, row_off, &left, &f, stream);
     if (rc != YC_OK) return rc;
     YC_REQUIRE(left == 0, YC_ERR_UNSUPPORTED, "yc_detect_fused: levels 0x%x do not fit the tcgen05 kernel: %s", left, g_err);
-    return launch_nms_tail(p, f.ws, out_rows, out_idx, out_counts, out_offsets, stream);
+    return YC_OK;
+}
+
+extern "C" int yc_nms_from_candidates(const yc_nms_params *p, void *workspace, size_t workspace_bytes, float *out_rows,
+                                      int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets, yc_stream_t stream_)
+{
+    YC_REQUIRE(p && workspace && out_rows && out_idx && out_counts && out_offsets, YC_ERR_INVALID,
+               "yc_nms_from_candidates: null argument");
+    YC_REQUIRE(p->bs > 0 && p->rows > 0 && p->nc > 0 && p->bs <= 65535, YC_ERR_INVALID, "yc_nms_from_candidates: bad shape");
+    YC_REQUIRE(!p->correct_boxes || p->image_hw, YC_ERR_INVALID, "yc_nms_from_candidates: correct_boxes needs image_hw");
+    void *base = (void *)round_up_sz((size_t)workspace, 256);
+    NmsWs ws = carve(base, p->bs, p->rows, p->nc);
+    YC_REQUIRE(ws.total_bytes + ((char *)base - (char *)workspace) <= workspace_bytes, YC_ERR_WORKSPACE,
+               "yc_nms_from_candidates: workspace %zu < %zu", workspace_bytes, ws.total_bytes + 256);
+    return launch_nms_tail(p, ws, out_rows, out_idx, out_counts, out_offsets, (cudaStream_t)stream_);
+}
+
+extern "C" int yc_detect_fused(const yc_head_desc *d, const yc_nms_params *p, void *workspace, size_t workspace_bytes,
+                               float *out_rows, int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets,
+                               yc_stream_t stream)
+{
+    YC_REQUIRE(out_rows && out_idx && out_counts && out_offsets, YC_ERR_INVALID, "yc_detect_fused: null argument");
+    const int rc = yc_detect_fused_head(d, p, workspace, workspace_bytes, stream);
+    if (rc != YC_OK) return rc;
+    return yc_nms_from_candidates(p, workspace, workspace_bytes, out_rows, out_idx, out_counts, out_offsets, stream);
 }
