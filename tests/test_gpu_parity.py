@@ -483,3 +483,24 @@ def test_fused_step_vs_oracle_pipeline():
         got = rows[off[b]:off[b + 1]].cpu().numpy()
         assert np.array_equal(got[:, 6], want[b][:, 6])
         np.testing.assert_allclose(got[:, :6], want[b][:, :6], rtol=1e-3, atol=1e-2)
+
+
+def test_fused_step_full_size_weight_resident():
+    """COCO head at 640x640, bs 8: CTAs process several consecutive K=256 tiles, so the weight-resident
+    mode of the TMA producer is exercised; fused == two-call path bit for bit."""
+    from yolo_continuous_b200.pipeline import PostBackbone
+    ch, shapes, bs = (256, 512, 1024), [(80, 80), (40, 40), (20, 20)], 8
+    head = _bench_like_head(80, ch, 8).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    xs = [torch.randn(bs, c, h, w, generator=g, device=DEV).to(torch.bfloat16) for c, (h, w) in zip(ch, shapes)]
+    res = []
+    for fused in (True, False):
+        pipe = PostBackbone(head, bs, shapes, torch.bfloat16, (640, 640), (512, 773), True, 0.25, 0.45, DEV,
+                            use_graph=False, fused=fused)
+        rows, idx, counts, offsets = pipe.run_device(xs)
+        assert pipe.fused == fused
+        tot = int(offsets[-1])
+        res.append((rows[:tot].clone(), idx[:tot].clone(), counts.clone(), offsets.clone()))
+    assert int(res[0][3][-1]) > 100
+    for a_, b_ in zip(res[0], res[1]):
+        assert torch.equal(a_, b_)

@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libyc_b200.so")
+LIB_PATH = os.environ.get("YC_LIB_PATH") or os.path.join(HERE, "csrc", "libyc_b200.so")  # env override: kernel experiments
 
 YC_MAX_LEVELS = 4
 YC_MAX_ANCHORS = 4

@@ -4,9 +4,9 @@
 //
 // Formulation.  Per level the conv is D[p, c] = sum_k X[b, k, p] * W[c, k]  (p = pixel, c = a*no + o).
 //   A operand = feature map, straight from NCHW: pixels are contiguous, so A is "MN-major"; a TMA box
-//               {64 px, 32 k} lands as [32 k-rows][128 B] with the 128-byte swizzle -- the canonical
+//               {64 px, 64 k} lands as [64 k-rows][128 B] with the 128-byte swizzle -- the canonical
 //               MN-major SWIZZLE_128B UMMA layout.  Two boxes make the 128-pixel M tile.
-//   B operand = packed bf16 weights [Npad, K], K-major, TMA box {32 k, Npad} with the 64-byte swizzle.
+//   B operand = packed bf16 weights [Npad, K], K-major, TMA box {64 k, Npad} with the 128-byte swizzle.
 //   D         = 128 lanes (pixels) x Npad fp32 columns in TMEM, double buffered (2 x 256 columns).
 // With pixels on TMEM lanes, one epilogue thread owns one output row (b, a, y, x, 0..no): a warp's
 // 32 rows are ONE contiguous span of z (32*no*4 bytes), staged in shared memory and written with a
@@ -16,21 +16,28 @@
 // warp 3 idle, then 4 epilogue warps per anchor (warp%4 = TMEM lane quadrant).
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
 // round-robin tile scheduler over all (level, image, 128-pixel block) tiles, heaviest level first.
+#include <stdlib.h>
+
 #include "yc_common.cuh"
 #include "yc_nms.cuh"
 #include "yc_sm100.cuh"
+
+#ifdef YC_EXPERIMENT_NO_SB
+#define YC_SB(p) make_float2(1.0f, 0.0f)
+#else
+#define YC_SB(p) __ldg(p)
+#endif
 
 namespace yc {
 
 using namespace sm100;
 
 constexpr int TC_BM = 128;       // pixels per tile (UMMA M)
-constexpr int TC_BK = 32;        // k per pipeline stage
-constexpr int TC_MAX_STAGES = 8;   // 4 when the z slabs occupy shared memory, 8 in the fused mode
+constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_MAX_N = 256;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;        // 8 KB: two {64 px, 32 k} bf16 boxes
-constexpr int TC_B_BYTES_MAX = TC_MAX_N * TC_BK * 2; // 16 KB
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES_MAX;
+// k per pipeline stage is a template parameter BK (64 or 128):
+//   A stage = two {64 px, BK k} bf16 boxes (BK*128 B each); B stage = BK/64 boxes {64 k, Npad} (32 KB each)
+constexpr int TC_B_BOX_BYTES = TC_MAX_N * 64 * 2;    // 32 KB
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_NON_EPI_THREADS = 128;
 
@@ -54,8 +61,9 @@ struct TcParams {
     int write_z;               // 0 for YC_HEAD_RAW
     float *z;
     uint32_t idesc;
-    uint32_t b_bytes;          // npad * TC_BK * 2
+    uint32_t b_box_bytes;      // npad * 64 * 2: bytes one weight box brings
     uint32_t slab_bytes;       // 32 * no * 4, rounded up to 16 (0 in the fused mode)
+    int debug;                 // YC_TC_DEBUG bits (timing experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA
     int stages;                // depth of the smem ring
     // fused mode (yc_detect_fused): the epilogue thresholds and emits NMS candidates, z is never written
     int fused;
@@ -138,10 +146,14 @@ __device__ __forceinline__ void cls_chunk(uint32_t taddr, int c, const float2 *_
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        const float2 s_b = __ldg(sb + c + j);
+        const float2 s_b = YC_SB(sb + c + j);
         float t = fmaf(__uint_as_float(v[j]), s_b.x, s_b.y);
-        if (EXACT) t = sigmoidf_fast(t); // compare what z would hold (first maximum of the sigmoids, torch.max)
-        if (t > bestv) { bestv = t; besti = c + j - 5; }
+        if (EXACT) {
+            t = sigmoidf_fast(t); // compare what z would hold (first maximum of the sigmoids, torch.max)
+            if (t > bestv) { bestv = t; besti = c + j - 5; }
+        } else {
+            bestv = fmaxf(bestv, t); // quick pass: only the largest class logit is needed
+        }
     }
 }
 
@@ -156,6 +168,33 @@ __device__ __forceinline__ void cls_scan(uint32_t taddr, int no, const float2 *_
     if (rem & 2) { cls_chunk<2, EXACT>(taddr, c, sb, bestv, besti); c += 2; }
     if (rem & 1) { cls_chunk<1, EXACT>(taddr, c, sb, bestv, besti); }
 }
+
+
+// survivors of the objectness filter park their raw class accumulators in the warp's shared-memory queue
+template <int W>
+__device__ __forceinline__ void queue_chunk(uint32_t taddr, int c, bool pass, float *__restrict__ qrow)
+{
+    uint32_t v[W];
+    TmemLd<W>::ld(taddr + (uint32_t)c, v);
+    tmem_ld_wait();
+    if (pass) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) qrow[c - 5 + j] = __uint_as_float(v[j]);
+    }
+}
+
+__device__ __forceinline__ void queue_classes(uint32_t taddr, int no, bool pass, float *__restrict__ qrow)
+{
+    int c = 5;
+    for (; c + 16 <= no; c += 16) queue_chunk<16>(taddr, c, pass, qrow);
+    const int rem = no - c;
+    if (rem & 8) { queue_chunk<8>(taddr, c, pass, qrow); c += 8; }
+    if (rem & 4) { queue_chunk<4>(taddr, c, pass, qrow); c += 4; }
+    if (rem & 2) { queue_chunk<2>(taddr, c, pass, qrow); c += 2; }
+    if (rem & 1) { queue_chunk<1>(taddr, c, pass, qrow); }
+}
+
+constexpr int TC_QUEUE_ROWS = 4; // survivors per warp and tile handled through the queue; more -> in-register scan
 
 // warp-cooperative write of `nv` finished rows from the slab to global memory
 __device__ __forceinline__ void slab_store(float *__restrict__ gdst, const float *__restrict__ slab, int nv, int no, int lane)
@@ -173,9 +212,13 @@ __device__ __forceinline__ void slab_store(float *__restrict__ gdst, const float
     }
 }
 
+template <int BK>
 __global__ void __launch_bounds__(TC_NON_EPI_THREADS + 128 * 3, 1)
 head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
+    constexpr int TC_BK = BK;
+    constexpr int TC_A_BYTES = TC_BM * BK * 2;
+    constexpr int TC_STAGE_BYTES = TC_A_BYTES + (BK / 64) * TC_B_BOX_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // carve: [stages: A|B] (1024-aligned) [slabs] [barriers]
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -215,23 +258,44 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    // The producer and the MMA issuer are single threads; each k-block costs them a fixed ~0.3 us of
+    // mbarrier / tcgen05.commit round trips (measured: the bare synchronisation skeleton of this kernel
+    // with K=32 stages took 88 us for the C2 batch), so a stage carries K=64: four MMAs per round trip.
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            // Weight residency: when a level has exactly n_stages k-blocks and a tile starts at ring slot 0,
+            // k-block kb of W always lands in slot kb.  After one such tile the B halves of all slots hold
+            // the whole W of that level, so the following tiles of the same level load only A (the MMA
+            // thread is unaware: it reads B from the slot as usual; a slot's B half is only ever written
+            // by this thread, after the slot's empty barrier).
+            int resident_lv = -1;
             for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
                 const TileCoord tc = tile_coord(P, t);
                 const int nkb = (P.lv[tc.lv].K + TC_BK - 1) / TC_BK;
+                const bool aligned = nkb == n_stages && stage == 0;
+                const bool load_b = !(aligned && resident_lv == tc.lv);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t *sa = stage_base + stage * TC_STAGE_BYTES, *sb = sa + TC_A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)TC_A_BYTES + P.b_bytes);
-                    tma_load_3d(sa, &maps.a[tc.lv], &full_bar[stage], tc.p0, kb * TC_BK, tc.b);
-                    tma_load_3d(sa + TC_A_BYTES / 2, &maps.a[tc.lv], &full_bar[stage], tc.p0 + 64, kb * TC_BK, tc.b);
-                    tma_load_2d(sb, &maps.b[tc.lv], &full_bar[stage], kb * TC_BK, 0);
+                    if (P.debug & 4) {
+                        mbar_arrive(&full_bar[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage],
+                                              (uint32_t)TC_A_BYTES + (load_b ? (BK / 64) * P.b_box_bytes : 0u));
+                        tma_load_3d(sa, &maps.a[tc.lv], &full_bar[stage], tc.p0, kb * TC_BK, tc.b);
+                        tma_load_3d(sa + TC_A_BYTES / 2, &maps.a[tc.lv], &full_bar[stage], tc.p0 + 64, kb * TC_BK, tc.b);
+                        if (load_b) {
+#pragma unroll
+                            for (int j = 0; j < BK / 64; ++j)
+                                tma_load_2d(sb + j * TC_B_BOX_BYTES, &maps.b[tc.lv], &full_bar[stage], kb * TC_BK + j * 64, 0);
+                        }
+                    }
                     if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                 }
+                resident_lv = aligned ? tc.lv : -1;
             }
         }
     } else if (warp == 1) {
@@ -253,12 +317,13 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     const uint32_t sa = smem_addr(stage_base + stage * TC_STAGE_BYTES), sb = sa + TC_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
-                        // A: MN-major SW128: 64-px chunks LBO = 4096 B apart, 8-k groups SBO = 1024 B apart;
-                        //    one k16 step = two 8-k groups = 2048 B
+                        // A: MN-major SW128: 64-px chunks LBO = BK*128 B apart (one {64 px, BK k} box each),
+                        //    8-k groups SBO = 1024 B apart; one k16 step = two 8-k groups = 2048 B
                         const uint64_t da = smem_desc(sa + k * 2048, TC_A_BYTES / 2, 1024, SWZ_128B);
-                        // B: K-major SW64: 8-row groups SBO = 512 B apart; k16 step = 32 B inside the 64-B row
-                        const uint64_t db = smem_desc(sb + k * 32, 16, 512, SWZ_64B);
-                        mma_f16(tmem_d, da, db, P.idesc, (uint32_t)((kb | k) != 0));
+                        // B: K-major SW128, one box per 64 k: 8-row groups SBO = 1024 B apart; k16 step = 32 B
+                        //    inside the 128-B row
+                        const uint64_t db = smem_desc(sb + (k / 4) * TC_B_BOX_BYTES + (k % 4) * 32, 16, 1024, SWZ_128B);
+                        if (!(P.debug & 2)) mma_f16(tmem_d, da, db, P.idesc, (uint32_t)((kb | k) != 0));
                     }
                     mma_commit(&empty_bar[stage]); // frees the smem slot when these MMAs retire
                     if (kb == nkb - 1) mma_commit(&tfull_bar[buf]);
@@ -289,8 +354,14 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
             mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
+            if (P.debug & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                continue;
+            }
             if (P.fused) {
-                // box + objectness logits (columns 0..4), then the running maximum of the class logits
+                // box + objectness logits (columns 0..4), then the largest class logit
                 uint32_t v4[4], v1[1];
                 TmemLd<4>::ld(taddr, v4);
                 TmemLd<1>::ld(taddr + 4u, v1);
@@ -298,20 +369,20 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 float tb[5];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float2 s_b = __ldg(sb + j);
+                    const float2 s_b = YC_SB(sb + j);
                     tb[j] = fmaf(__uint_as_float(v4[j]), s_b.x, s_b.y);
                 }
                 {
-                    const float2 s_b = __ldg(sb + 4);
+                    const float2 s_b = YC_SB(sb + 4);
                     tb[4] = fmaf(__uint_as_float(v1[0]), s_b.x, s_b.y);
                 }
-                float bestv = -INFINITY;
-                int besti = 0;
-                cls_scan<false>(taddr, no, sb, bestv, besti);
+                // Early reject on objectness alone: class scores are sigmoids (<= 1), so obj >= conf is necessary
+                // for obj*cls >= conf.  At detection thresholds >99% of rows stop here after 5 columns; only
+                // warps holding a survivor scan the class columns (exactly as the z path would see them).
                 const float obj = sigmoidf_fast(tb[4]);
-                bool pass = lane < nv && __fmul_rn(obj, sigmoidf_fast(bestv)) >= P.conf;
+                bool pass = lane < nv && obj >= P.conf;
                 if (__any_sync(0xffffffffu, pass)) {
-                    // rare: redo the class scan on the sigmoid values so that ties resolve exactly as on z
+                    // class scan on the sigmoid values: first maximum, ties resolve exactly as on z
                     float bv = -1.0f;
                     int best = 0;
                     cls_scan<true>(taddr, no, sb, bv, best);
@@ -393,11 +464,15 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     YC_REQUIRE(enc != nullptr, YC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
 
     const uint32_t slab_bytes = fused ? 0u : (uint32_t)round_up(32 * d->no * 4, 16);
+    // fused mode (no z slabs in shared memory): K=128 per stage, 2 stages; otherwise K=64, as many stages as fit
+    int bk = fused ? 128 : 64;
+    { const char *e = getenv("YC_TC_BK"); if (e && (atoi(e) == 64 || atoi(e) == 128)) bk = atoi(e); }
+    const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * TC_B_BOX_BYTES;
+    const size_t fixed = 1024 + (size_t)4 * d->na * slab_bytes + 256;
     int stages = TC_MAX_STAGES;
-    while (stages > 2 && 1024 + (size_t)stages * TC_STAGE_BYTES + (size_t)4 * d->na * slab_bytes + 256 > 227 * 1024) --stages;
-    const size_t smem_bytes = 1024 + (size_t)stages * TC_STAGE_BYTES + (size_t)4 * d->na * slab_bytes + 256;
+    while (stages > 2 && fixed + (size_t)stages * stage_bytes > 227 * 1024) --stages;
+    const size_t smem_bytes = fixed + (size_t)stages * stage_bytes;
     YC_REQUIRE(smem_bytes <= 227 * 1024, YC_ERR_UNSUPPORTED, "tcgen05 head: needs %zu bytes of shared memory", smem_bytes);
-
     // which levels fit: TMA needs 16-byte aligned bases and row pitches
     unsigned fit = 0;
     for (int i = 0; i < d->nl; ++i) {
@@ -428,9 +503,10 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     P.write_z = d->kind == YC_HEAD_IDETECT ? 1 : 0;
     P.z = d->z;
     P.idesc = instr_desc_f16(/*bf16*/ 1, /*A MN-major*/ 1, /*B K-major*/ 0, TC_BM, (uint32_t)npad);
-    P.b_bytes = (uint32_t)npad * TC_BK * 2;
+    P.b_box_bytes = (uint32_t)npad * 64 * 2;
     P.slab_bytes = slab_bytes;
     P.stages = stages;
+    { const char *e = getenv("YC_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
     if (fused) {
         P.fused = 1; P.nc = fused->nc; P.conf = fused->conf; P.div_w = fused->div_w; P.div_h = fused->div_h;
         P.ws = fused->ws;
@@ -452,21 +528,21 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         L.stride = lv.stride;
         for (int j = 0; j < YC_MAX_ANCHORS * 2; ++j) L.anchor_wh[j] = lv.anchor_wh[j];
         tiles += d->bs * L.tiles_per_img;
-        {   // A: X [bs, K, HW] bf16, box {64 px, 32 k, 1}
+        {   // A: X [bs, K, HW] bf16, box {64 px, 64 k, 1}
             cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)lv.K, (cuuint64_t)d->bs};
             cuuint64_t gstr[2] = {(cuuint64_t)HW * 2, (cuuint64_t)HW * lv.K * 2};
-            cuuint32_t box[3] = {64, TC_BK, 1}, est[3] = {1, 1, 1};
+            cuuint32_t box[3] = {64, (cuuint32_t)bk, 1}, est[3] = {1, 1, 1};
             CUresult r = enc(&maps.a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)lv.x, gdim, gstr, box, est,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             YC_REQUIRE(r == CUDA_SUCCESS, YC_ERR_CUDA, "cuTensorMapEncodeTiled(A, level %d) failed: %d", i, (int)r);
         }
-        {   // B: W [Npad, K] bf16, box {32 k, Npad}
+        {   // B: W [Npad, K] bf16, box {64 k, Npad}
             cuuint64_t gdim[2] = {(cuuint64_t)lv.K, (cuuint64_t)npad};
             cuuint64_t gstr[1] = {(cuuint64_t)lv.K * 2};
-            cuuint32_t box[2] = {TC_BK, (cuuint32_t)npad}, est[2] = {1, 1};
+            cuuint32_t box[2] = {64, (cuuint32_t)npad}, est[2] = {1, 1};
             CUresult r = enc(&maps.b[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)bv.w_bf, gdim, gstr, box, est,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             YC_REQUIRE(r == CUDA_SUCCESS, YC_ERR_CUDA, "cuTensorMapEncodeTiled(B, level %d) failed: %d", i, (int)r);
         }
@@ -478,13 +554,15 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         YC_CUDA(cudaGetDevice(&dev));
         YC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        YC_CUDA(cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    head_tc_kernel<<<grid, TC_NON_EPI_THREADS + 128 * d->na, smem_bytes, stream>>>(maps, P);
+    const int threads = TC_NON_EPI_THREADS + 128 * d->na;
+    if (bk == 128) {
+        YC_CUDA(cudaFuncSetAttribute(head_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        head_tc_kernel<128><<<grid, threads, smem_bytes, stream>>>(maps, P);
+    } else {
+        YC_CUDA(cudaFuncSetAttribute(head_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        head_tc_kernel<64><<<grid, threads, smem_bytes, stream>>>(maps, P);
+    }
     YC_CUDA(cudaGetLastError());
     return YC_OK;
 }

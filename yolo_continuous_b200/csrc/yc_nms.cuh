@@ -85,6 +85,19 @@ __device__ __forceinline__ void emit_candidates(bool pass, int b, int r, int row
     }
 }
 
+// single-lane form of emit_candidates (used where one lane owns a finished candidate)
+__device__ __forceinline__ void emit_one(int b, int r, int rows, int nc, float x1, float y1, float x2, float y2, float obj,
+                                         float conf_cls, float score, int cls, const NmsWs &ws)
+{
+    const size_t ib = (size_t)b * rows;
+    const int slot = atomicAdd(&ws.cand_count[b], 1);
+    ws.box[ib + r] = make_float4(x1, y1, x2, y2);
+    ws.oc[ib + r] = make_float2(obj, conf_cls);
+    ws.key_unsorted[ib + slot] = make_key(score, r);
+    ws.cls_unsorted[ib + slot] = cls;
+    atomicAdd(&ws.hist[(size_t)b * nc + cls], 1);
+}
+
 // xywh (optionally divided by the input size) -> corners, in the reference's operation order
 // (detect.py:98-103): x1 = cx - w/2 ...
 __device__ __forceinline__ void xywh_to_corners(float cx, float cy, float bw, float bh, float div_w, float div_h, float &x1,
