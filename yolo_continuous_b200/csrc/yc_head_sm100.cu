@@ -62,7 +62,7 @@ struct TcParams {
     float *z;
     uint32_t idesc;
     uint32_t b_box_bytes;      // npad * 64 * 2: bytes one weight box brings
-    uint32_t slab_bytes;       // 32 * no * 4, rounded up to 16 (0 in the fused mode)
+    uint32_t slab_bytes;       // per epilogue warp: 32*no*4 (z slab) or TC_QUEUE_ROWS*nc*4 (fused survivor queue)
     int debug;                 // YC_TC_DEBUG bits (timing experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA
     int stages;                // depth of the smem ring
     // fused mode (yc_detect_fused): the epilogue thresholds and emits NMS candidates, z is never written
@@ -381,8 +381,54 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 // warps holding a survivor scan the class columns (exactly as the z path would see them).
                 const float obj = sigmoidf_fast(tb[4]);
                 bool pass = lane < nv && obj >= P.conf;
-                if (__any_sync(0xffffffffu, pass)) {
-                    // class scan on the sigmoid values: first maximum, ties resolve exactly as on z
+                const unsigned surv = __ballot_sync(0xffffffffu, pass);
+                const int n_surv = __popc(surv);
+                if (n_surv > 0 && n_surv <= TC_QUEUE_ROWS) {
+                    // Few survivors (the common case): copy their class accumulators to shared memory, hand the
+                    // TMEM buffer back at once, then scan the classes with the 32 lanes spread over the classes.
+                    float *q = slab; // per-warp queue [TC_QUEUE_ROWS][nc]
+                    const int nc = P.nc;
+                    queue_classes(taddr, no, pass, q + __popc(surv & ((1u << lane) - 1u)) * nc);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                    unsigned left = surv;
+                    for (int sidx = 0; sidx < n_surv; ++sidx) {
+                        const int src = __ffs(left) - 1;
+                        left &= left - 1;
+                        float bv = -1.0f;
+                        int best = 0;
+                        for (int c = lane; c < nc; c += 32) { // ascending classes per lane: strict > keeps the first
+                            const float2 s_b = __ldg(sb + 5 + c);
+                            const float sg = sigmoidf_fast(fmaf(q[sidx * nc + c], s_b.x, s_b.y));
+                            if (sg > bv) { bv = sg; best = c; }
+                        }
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) { // larger value wins, ties go to the smaller class
+                            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                            const int oi = __shfl_xor_sync(0xffffffffu, best, off);
+                            if (ov > bv || (ov == bv && oi < best)) { bv = ov; best = oi; }
+                        }
+                        const float o_s = __shfl_sync(0xffffffffu, obj, src);
+                        const float t0 = __shfl_sync(0xffffffffu, tb[0], src), t1 = __shfl_sync(0xffffffffu, tb[1], src);
+                        const float t2 = __shfl_sync(0xffffffffu, tb[2], src), t3 = __shfl_sync(0xffffffffu, tb[3], src);
+                        const float score = __fmul_rn(o_s, bv);
+                        if (lane == 0 && score >= P.conf) {
+                            const int ps = prow0 + src;
+                            const float cx = decode_xy(sigmoidf_fast(t0), (float)(ps % L.nx), L.stride);
+                            const float cy = decode_xy(sigmoidf_fast(t1), (float)(ps / L.nx), L.stride);
+                            const float bw = decode_wh(sigmoidf_fast(t2), aw), bh = decode_wh(sigmoidf_fast(t3), ah);
+                            float x1, y1, x2, y2;
+                            xywh_to_corners(cx, cy, bw, bh, P.div_w, P.div_h, x1, y1, x2, y2);
+                            emit_one(tc.b, L.row_off + a * L.HW + ps, P.rows_total, nc, x1, y1, x2, y2, o_s, bv, score, best,
+                                     P.ws);
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                if (n_surv > 0) {
+                    // many survivors (low thresholds): class scan in registers, first maximum of the sigmoids
                     float bv = -1.0f;
                     int best = 0;
                     cls_scan<true>(taddr, no, sb, bv, best);
@@ -463,9 +509,12 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     EncodeTiledFn enc = encode_tiled();
     YC_REQUIRE(enc != nullptr, YC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
 
-    const uint32_t slab_bytes = fused ? 0u : (uint32_t)round_up(32 * d->no * 4, 16);
-    // fused mode (no z slabs in shared memory): K=128 per stage, 2 stages; otherwise K=64, as many stages as fit
-    int bk = fused ? 128 : 64;
+    // per epilogue warp: z slab (32 rows) or, in the fused mode, the survivor queue (TC_QUEUE_ROWS x nc floats)
+    const uint32_t slab_bytes = fused ? (uint32_t)round_up(TC_QUEUE_ROWS * (d->no - 5) * 4, 16)
+                                      : (uint32_t)round_up(32 * d->no * 4, 16);
+    // K=64 per stage: 4 stages in the fused mode (no z slabs in shared memory), 2 next to the slabs.
+    // (K=128 x 2 stages measured 6 us slower on the C2 batch; YC_TC_BK overrides for experiments.)
+    int bk = 64;
     { const char *e = getenv("YC_TC_BK"); if (e && (atoi(e) == 64 || atoi(e) == 128)) bk = atoi(e); }
     const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * TC_B_BOX_BYTES;
     const size_t fixed = 1024 + (size_t)4 * d->na * slab_bytes + 256;
