@@ -67,3 +67,40 @@ def test_shard_range_covers_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _worker_fixed(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from yolo_continuous_b200.parallel import DetectionGather
+    bs, cap = 3, 8
+    hdr_ints = (2 * bs + 1 + 3) // 4 * 4
+    msg = torch.zeros(hdr_ints * 4 + cap * 28, dtype=torch.uint8)
+    hdr = msg[:hdr_ints * 4].view(torch.int32)
+    counts = torch.tensor([1, 0, 2 + rank], dtype=torch.int32)
+    hdr[:bs] = counts
+    hdr[bs:2 * bs + 1] = torch.tensor([0] + counts.cumsum(0).tolist(), dtype=torch.int32)
+    rows = msg[hdr_ints * 4:].view(torch.float32).view(cap, 7)
+    rows[:int(counts.sum()), 0] = torch.arange(int(counts.sum())) + 100.0 * rank
+    g = DetectionGather(msg.numel(), "cpu")
+    slot = g.gather_async(msg)
+    g.wait()
+    ok = True
+    for r, (c, total, rr) in enumerate(g.unpack(slot, bs, hdr_ints, cap)):
+        ok &= c.tolist() == [1, 0, 2 + r] and int(total) == 3 + r
+        ok &= rr[:int(total), 0].tolist() == [100.0 * r + i for i in range(3 + r)]
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_fixed_size_detection_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_fixed, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    assert all(r[1] for r in res), res

@@ -32,3 +32,48 @@ def gather_detections(rows, counts, group=None):
     dist.all_gather_into_tensor(out, pad, group=group)
     out = out.view(world, tmax, rows.shape[1])
     return [out[r, :int(totals[r])] for r in range(world)], cnt_all
+
+
+class DetectionGather:
+    """Allocation-free, host-sync-free exchange for the steady state: every rank contributes one fixed-size
+    message (the header with per-image counts/offsets + the first `gather_rows` detection rows, exactly the
+    prefix PostBackbone.message() returns) and one `all_gather_into_tensor` delivers all of them.  On CUDA
+    the collective runs on a side stream behind an event, so with double-buffered outputs the exchange of
+    step i overlaps step i+1.  A rank whose detections exceed `gather_rows` is visible in its header
+    (offsets[-1] > gather_rows); callers fetch the remainder with `gather_detections`."""
+
+    def __init__(self, msg_bytes, device, group=None, n_bufs=2):
+        self.group, self.world = group, dist.get_world_size(group)
+        self.msg_bytes = msg_bytes
+        self.out = [torch.empty((self.world * msg_bytes,), dtype=torch.uint8, device=device) for _ in range(n_bufs)]
+        self.slot = 0
+        self.cuda = torch.device(device).type == "cuda"
+        self.stream = torch.cuda.Stream(device=device) if self.cuda else None
+
+    def gather_async(self, msg):
+        assert msg.numel() == self.msg_bytes and msg.dtype == torch.uint8
+        self.slot = (self.slot + 1) % len(self.out)
+        dst = self.out[self.slot]
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ev)
+                dist.all_gather_into_tensor(dst, msg, group=self.group)
+        else:
+            dist.all_gather_into_tensor(dst, msg, group=self.group)
+        return self.slot
+
+    def wait(self):
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+    def unpack(self, slot, bs, hdr_ints, gather_rows):
+        """-> list over ranks of (counts [bs], total, rows [min(total, gather_rows), 7]) views (no copy)."""
+        res = []
+        for r in range(self.world):
+            m = self.out[slot][r * self.msg_bytes:(r + 1) * self.msg_bytes]
+            hdr = m[:hdr_ints * 4].view(torch.int32)
+            rows = m[hdr_ints * 4:].view(torch.float32).view(gather_rows, 7)
+            res.append((hdr[:bs], hdr[2 * bs], rows))
+        return res

@@ -20,7 +20,7 @@ from . import _lib
 class PostBackbone:
     def __init__(self, head, bs, shapes, dtype=torch.bfloat16, input_shape=(640, 640), image_shape=(640, 640),
                  letterbox_image=True, conf_thres=0.25, nms_thres=0.45, device="cuda:0", use_graph=True,
-                 spec_rows=65536, fused=True):
+                 spec_rows=65536, fused=True, double_buffer=False):
         self.head, self.bs, self.shapes = head, bs, [tuple(s) for s in shapes]
         self.device = torch.device(device)
         self.dtype = dtype
@@ -34,10 +34,18 @@ class PostBackbone:
         with torch.cuda.device(dev):
             self.x_dev = [torch.empty((bs, c, h, w), dtype=dtype, device=dev) for c, (h, w) in zip(self.ch, self.shapes)]
             self.z = torch.empty((bs, self.rows, self.no), dtype=torch.float32, device=dev)
-            self.out_rows = torch.empty((bs * self.rows, 7), dtype=torch.float32, device=dev)
+            # Output message(s): [counts (bs) | offsets (bs+1) | pad] int32 header followed by the detection rows
+            # [bs*rows, 7] fp32 in ONE allocation, so that a fixed-size prefix (header + the first `gather_rows`
+            # rows) can be sent as a single all-gather / D2H copy.  Two of them when double-buffered (the
+            # multi-GPU exchange of step i overlaps step i+1).
+            self.hdr_ints = (2 * bs + 1 + 3) // 4 * 4
+            self.n_bufs = 2 if double_buffer else 1
+            self.msgs = [torch.empty((self.hdr_ints * 4 + bs * self.rows * 28,), dtype=torch.uint8, device=dev)
+                         for _ in range(self.n_bufs)]
+            self.metas = [m[:self.hdr_ints * 4].view(torch.int32)[:2 * bs + 1] for m in self.msgs]
+            self.rows_bufs = [m[self.hdr_ints * 4:].view(torch.float32).view(bs * self.rows, 7) for m in self.msgs]
+            self.cur = 0
             self.out_idx = torch.empty((bs * self.rows,), dtype=torch.int32, device=dev)
-            # counts [bs] and offsets [bs+1] share one buffer so that a single D2H copy fetches both
-            self.meta = torch.empty((2 * bs + 1,), dtype=torch.int32, device=dev)
             self.ws = torch.empty(_lib.lib.yc_nms_workspace_bytes(bs, self.rows, self.nc) + 1024, dtype=torch.uint8,
                                   device=dev)
             hw = np.asarray(image_shape, dtype=np.int32).reshape(-1, 2)
@@ -75,9 +83,20 @@ class PostBackbone:
         # otherwise head kernel (writes z) + threshold/compaction + the same 5.  (memsets are not kernels)
         self.fused = fused and dtype == torch.bfloat16
         self.kernels_per_step = 6 if self.fused else 7
-        self.graph = None
+        self._graphs = {}
         self.use_graph = use_graph
-        self._graph_ptrs = None
+
+    @property
+    def meta(self):
+        return self.metas[self.cur]
+
+    @property
+    def out_rows(self):
+        return self.rows_bufs[self.cur]
+
+    def message(self, gather_rows):
+        """Fixed-size prefix of the current output buffer: header + the first `gather_rows` detection rows."""
+        return self.msgs[self.cur][:self.hdr_ints * 4 + gather_rows * 28]
 
     # ---- device path -----------------------------------------------------------------------
     def _launch(self, features):
@@ -104,18 +123,23 @@ class PostBackbone:
         """features: list of [bs, ch_i, H_i, W_i] device tensors.  Returns device views
         (rows [bs*rows,7] capacity, idx, counts [bs], offsets [bs+1])."""
         with torch.cuda.device(self.device):
-            ptrs = tuple(x.data_ptr() for x in features)
+            if self.n_bufs > 1:
+                self.cur ^= 1
+            ptrs = tuple(x.data_ptr() for x in features) + (self.cur,)
             if not self.use_graph:
                 self._launch(features)
             else:
-                if self.graph is None or self._graph_ptrs != ptrs:
+                g = self._graphs.get(ptrs)
+                if g is None:
                     self._launch(features)          # warm-up outside capture (lazy module/attribute setup)
                     torch.cuda.current_stream().synchronize()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         self._launch(features)
-                    self.graph, self._graph_ptrs = g, ptrs
-                self.graph.replay()
+                    if len(self._graphs) > 8:
+                        self._graphs.clear()
+                    self._graphs[ptrs] = g
+                g.replay()
         bs = self.bs
         return self.out_rows, self.out_idx, self.meta[:bs], self.meta[bs:]
 
