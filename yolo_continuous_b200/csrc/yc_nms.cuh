@@ -18,6 +18,7 @@ struct NmsWs {
     int *hist;                      // [bs*nc] candidates per (image, class)
     int *cursor;                    // [bs*nc]
     int *kept_count;                // [bs*nc]
+    int *img_total;                 // [bs] kept detections of an image + 1 once known (0 = not yet): chained scan
     int *seg_off;                   // [bs*nc]
     int *kept_off;                  // [bs*nc]
     size_t counters_bytes;
@@ -42,6 +43,7 @@ static inline NmsWs carve(void *base, int bs, int rows, int nc)
     w.hist = (int *)take(s * 4);
     w.cursor = (int *)take(s * 4);
     w.kept_count = (int *)take(s * 4);
+    w.img_total = (int *)take((size_t)bs * 4);
     w.counters = (int *)c0;
     w.counters_bytes = (size_t)(p - c0);
     w.seg_off = (int *)take(s * 4);

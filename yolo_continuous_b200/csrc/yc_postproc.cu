@@ -97,17 +97,29 @@ __global__ void __launch_bounds__(TC_ROWS) threshold_compact_kernel(float *__res
     emit_candidates(pass, b, r, rows, nc, x1, y1, x2, y2, obj, bv, score, best, ws);
 }
 
-// ---- K2: per-image exclusive scan of the class histogram ----------------------------------------
-__global__ void __launch_bounds__(256) segment_offsets_kernel(int nc, NmsWs ws)
+// ---- K2: class-histogram scan + bucket scatter --------------------------------------------------------
+// grid (ceil(rows / BUCKET_SLOTS), bs).  Every CTA of an image rescans the image's class histogram (nc
+// values, trivial) into shared memory, CTA 0 publishes it as seg_off, and each CTA moves its slice of the
+// image's candidate keys into their class buckets.
+constexpr int BUCKET_SLOTS = 4096;
+constexpr int BUCKET_SMEM_NC = 1024;
+
+__global__ void __launch_bounds__(256) bucket_kernel(int rows, int nc, NmsWs ws)
 {
+    __shared__ int s_off[BUCKET_SMEM_NC];
     __shared__ int warp_tot[8];
     __shared__ int carry_s;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = ws.cand_count[b];
+    const int s0 = blockIdx.x * BUCKET_SLOTS;
+    if (blockIdx.x != 0 && s0 >= n) return;
+    const size_t sb = (size_t)b * nc;
+    const bool first = blockIdx.x == 0;
     if (tid == 0) carry_s = 0;
     __syncthreads();
     for (int c0 = 0; c0 < nc; c0 += 256) {
         const int c = c0 + tid;
-        const int v = c < nc ? ws.hist[(size_t)b * nc + c] : 0;
+        const int v = c < nc ? ws.hist[sb + c] : 0;
         int inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -118,22 +130,22 @@ __global__ void __launch_bounds__(256) segment_offsets_kernel(int nc, NmsWs ws)
         __syncthreads();
         int pre = carry_s;
         for (int w = 0; w < wid; ++w) pre += warp_tot[w];
-        if (c < nc) ws.seg_off[(size_t)b * nc + c] = pre + inc - v;
+        if (c < nc) {
+            if (c < BUCKET_SMEM_NC) s_off[c] = pre + inc - v;
+            if (first || nc > BUCKET_SMEM_NC) ws.seg_off[sb + c] = pre + inc - v; // same value from every CTA
+        }
         __syncthreads();
         if (tid == 255) carry_s = pre + inc;
         __syncthreads();
     }
-}
-
-// ---- K3: move candidate keys into their class bucket ------------------------------------------------
-__global__ void __launch_bounds__(256) bucket_scatter_kernel(int rows, int nc, NmsWs ws)
-{
-    const int b = blockIdx.y, slot = blockIdx.x * 256 + threadIdx.x;
-    if (slot >= ws.cand_count[b]) return;
     const size_t ib = (size_t)b * rows;
-    const int cls = ws.cls_unsorted[ib + slot];
-    const int pos = ws.seg_off[(size_t)b * nc + cls] + atomicAdd(&ws.cursor[(size_t)b * nc + cls], 1);
-    ws.key_bucket[ib + pos] = ws.key_unsorted[ib + slot];
+    const int s1 = min(n, s0 + BUCKET_SLOTS);
+    for (int slot = s0 + tid; slot < s1; slot += 256) {
+        const int cls = ws.cls_unsorted[ib + slot];
+        const int off = cls < BUCKET_SMEM_NC ? s_off[cls] : ws.seg_off[sb + cls];
+        const int pos = off + atomicAdd(&ws.cursor[sb + cls], 1);
+        ws.key_bucket[ib + pos] = ws.key_unsorted[ib + slot];
+    }
 }
 
 // IoU test of torchvision's CPU nms kernel (third-party; call site detect.py:133):
@@ -161,32 +173,30 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, const flo
 // shared memory and warp 0 walks it: the lane owning the current 64-bit word finds the next
 // surviving box with ffs, all lanes OR that box's mask row into their word.  This is exactly the
 // sequential rule "keep i; suppress every later j with IoU(i,j) > thr" of the reference.
-__global__ void __launch_bounds__(NMS_NT) nms_segment_kernel(int rows, int nc, float thr_f, NmsWs ws)
-{
-    __shared__ unsigned long long skeys[SORT_SMEM];
-    __shared__ float4 sbox[NMS_NT];
-    __shared__ float4 skept[KEPT_SMEM];
-    __shared__ unsigned long long smask[NMS_NT][2];
-    __shared__ unsigned int sdead[NMS_NT / 32];
-    __shared__ int s_nkept;
+struct NmsSmem {
+    unsigned long long skeys[SORT_SMEM];
+    float4 sbox[NMS_NT];
+    float4 skept[KEPT_SMEM];
+    unsigned long long smask[NMS_NT][2];
+    unsigned int sdead[NMS_NT / 32];
+    int s_nkept;
+};
 
-    const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+// whole-CTA path for one segment of n >= 2 boxes (all NMS_NT threads call it)
+__device__ void nms_segment_cta(int b, int c, int n, int rows, int nc, float thr_f, const NmsWs &ws, NmsSmem &sm)
+{
+    unsigned long long *skeys = sm.skeys;
+    float4 *sbox = sm.sbox, *skept = sm.skept;
+    unsigned long long(*smask)[2] = sm.smask;
+    unsigned int *sdead = sm.sdead;
+    int &s_nkept = sm.s_nkept;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t seg = (size_t)b * nc + c;
-    const int n = ws.hist[seg];
-    if (n == 0) return; // kept_count stays 0
     const size_t ib = (size_t)b * rows;
     const int off = ws.seg_off[seg];
     unsigned long long *gkeys = ws.key_bucket + ib + off;
     int *kept_row = ws.kept_row + ib + off;
     float4 *kept_box = ws.kept_box + ib + off;
-
-    if (n == 1) {
-        if (tid == 0) {
-            kept_row[0] = (int)(gkeys[0] & 0xffffffffull);
-            ws.kept_count[seg] = 1;
-        }
-        return;
-    }
 
     unsigned long long *K = gkeys;
     if (n <= SORT_SMEM) {
@@ -276,69 +286,147 @@ __global__ void __launch_bounds__(NMS_NT) nms_segment_kernel(int rows, int nc, f
         __syncthreads();
     }
     if (tid == 0) ws.kept_count[seg] = s_nkept;
+    __syncthreads(); // shared state is reused by the next segment
 }
 
-// ---- K5: output offsets: per-image scan over classes, then scan over images --------------------
-__global__ void __launch_bounds__(1024) kept_scan_kernel(int bs, int nc, NmsWs ws, int *out_counts, int *out_offsets)
+
+// warp path for a segment of 2..32 boxes: shuffle bitonic sort of the keys (one per lane, +inf padding),
+// then the sequential greedy rule with the current box broadcast from its lane
+__device__ __forceinline__ void nms_segment_warp(int b, int c, int n, int rows, int nc, float thr_f, const NmsWs &ws)
 {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int b = wid; b < bs; b += 32) {
-        int running = 0;
-        for (int c0 = 0; c0 < nc; c0 += 32) {
-            const int c = c0 + lane;
-            const int v = c < nc ? ws.kept_count[(size_t)b * nc + c] : 0;
-            int inc = v;
+    const int lane = threadIdx.x & 31;
+    const size_t seg = (size_t)b * nc + c, ib = (size_t)b * rows;
+    const int off = ws.seg_off[seg];
+    unsigned long long key = lane < n ? ws.key_bucket[ib + off + lane] : ~0ull;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += t;
-            }
-            if (c < nc) ws.kept_off[(size_t)b * nc + c] = running + inc - v;
-            running += __shfl_sync(0xffffffffu, inc, 31);
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+            key = take_min ? (other < key ? other : key) : (other > key ? other : key);
         }
-        if (lane == 0) out_counts[b] = running;
     }
-    __syncthreads();
-    if (wid == 0) {
-        int running = 0;
-        for (int b0 = 0; b0 < bs; b0 += 32) {
-            const int b = b0 + lane;
-            const int v = b < bs ? out_counts[b] : 0;
-            int inc = v;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += t;
-            }
-            if (b < bs) out_offsets[b] = running + inc - v;
-            running += __shfl_sync(0xffffffffu, inc, 31);
+    const int row = (int)(key & 0xffffffffull);
+    float4 bx = make_float4(0, 0, 0, 0);
+    if (lane < n) bx = ws.box[ib + row];
+    bool alive = lane < n;
+    for (int i = 0; i < n - 1; ++i) {
+        const unsigned mask = __ballot_sync(0xffffffffu, alive);
+        if (!(mask >> i & 1u)) continue;
+        float4 bi;
+        bi.x = __shfl_sync(0xffffffffu, bx.x, i); bi.y = __shfl_sync(0xffffffffu, bx.y, i);
+        bi.z = __shfl_sync(0xffffffffu, bx.z, i); bi.w = __shfl_sync(0xffffffffu, bx.w, i);
+        if (lane > i && alive && iou_gt(bi, bx, thr_f)) alive = false;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, alive);
+    if (alive) ws.kept_row[ib + off + __popc(mask & ((1u << lane) - 1u))] = row;
+    if (lane == 0) ws.kept_count[seg] = __popc(mask);
+}
+
+// grid (ceil(nc / 4), bs), 4 warps: warp w owns class blockIdx.x*4 + w.  Segments of up to 32 boxes (the
+// common case at detection thresholds) are finished by their warp; larger ones are then processed one
+// after another by the whole CTA.
+__global__ void __launch_bounds__(NMS_NT) nms_segment_kernel(int rows, int nc, float thr_f, NmsWs ws)
+{
+    __shared__ NmsSmem sm;
+    __shared__ int big_n[NMS_NT / 32];
+    const int b = blockIdx.y, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (NMS_NT / 32) + wid;
+    int n = 0;
+    if (c < nc) n = ws.hist[(size_t)b * nc + c];
+    if (n == 1) {
+        if (lane == 0) {
+            const size_t ib = (size_t)b * rows;
+            const int off = ws.seg_off[(size_t)b * nc + c];
+            ws.kept_row[ib + off] = (int)(ws.key_bucket[ib + off] & 0xffffffffull);
+            ws.kept_count[(size_t)b * nc + c] = 1;
         }
-        if (lane == 0) out_offsets[bs] = running;
+    } else if (n >= 2 && n <= 32) {
+        nms_segment_warp(b, c, n, rows, nc, thr_f, ws);
+    }
+    if (lane == 0) big_n[wid] = n > 32 ? n : 0;
+    __syncthreads();
+    for (int w = 0; w < NMS_NT / 32; ++w) {
+        const int nb = big_n[w]; // uniform across the CTA
+        if (nb) nms_segment_cta(b, blockIdx.x * (NMS_NT / 32) + w, nb, rows, nc, thr_f, ws, sm);
     }
 }
 
-// ---- K6: assemble output rows (detect.py:121,137) and optionally undo the letterbox ---------------
-// yolo_correct_boxes (detect.py:140-142,147-165) is evaluated with numpy's promotion rules:
-// binary64 when letterbox_image is set (except box_hw *= scale, rounded back to binary32),
-// binary32 until the final multiply by the image shape otherwise; the result is stored as binary32.
+// ---- K5: per-image finish: kept-count scan, chained scan across images, output assembly -----------------
+// grid = bs.  CTA b scans its image's kept counts, publishes the image total (img_total[b] = total + 1) and
+// obtains its output offset by summing the totals of all earlier images, spinning on the few that are not
+// published yet (earlier CTAs are always scheduled first, so this cannot deadlock).  It then writes the
+// image's rows (reference detect.py:121,137) and optionally undoes the letterbox:
+// yolo_correct_boxes (detect.py:140-142,147-165) is evaluated with numpy's promotion rules: binary64 when
+// letterbox_image is set (except box_hw *= scale, rounded back to binary32), binary32 until the final
+// multiply by the image shape otherwise; the result is stored as binary32.
 struct CorrectParams {
     int enabled, letterbox, in_h, in_w;
     const int *image_hw;
     int image_hw_stride;
 };
 
-__global__ void __launch_bounds__(128) gather_kernel(int rows, int nc, NmsWs ws, const int *__restrict__ out_offsets,
-                                                     float *__restrict__ out_rows, int *__restrict__ out_idx,
-                                                     CorrectParams cp)
+constexpr int FINISH_NT = 128;
+constexpr int FINISH_SMEM_NC = 1024;
+
+__global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int nc, NmsWs ws, int *__restrict__ out_counts,
+                                                            int *__restrict__ out_offsets, float *__restrict__ out_rows,
+                                                            int *__restrict__ out_idx, CorrectParams cp)
 {
-    const int b = blockIdx.y, c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (c >= nc) return;
-    const size_t seg = (size_t)b * nc + c;
-    const int nk = ws.kept_count[seg];
-    if (nk == 0) return;
-    const size_t ib = (size_t)b * rows;
-    const int *kept_row = ws.kept_row + ib + ws.seg_off[seg];
-    const size_t obase = (size_t)out_offsets[b] + ws.kept_off[seg];
+    __shared__ int s_red[FINISH_NT / 32];
+    __shared__ int s_total, s_base;
+    __shared__ int s_koff[FINISH_SMEM_NC + 1], s_soff[FINISH_SMEM_NC];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t sb = (size_t)b * nc;
+    const bool flat = nc <= FINISH_SMEM_NC;
+    // exclusive scan of kept_count[b][:] -> kept_off (warp 0, 32 classes per step)
+    if (wid == 0) {
+        int running = 0;
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+            const int c = c0 + lane;
+            const int v = c < nc ? ws.kept_count[sb + c] : 0;
+            int inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (c < nc) {
+                ws.kept_off[sb + c] = running + inc - v;
+                if (flat) { s_koff[c] = running + inc - v; s_soff[c] = ws.seg_off[sb + c]; }
+            }
+            running += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {
+            s_total = running;
+            if (flat) s_koff[nc] = running;
+            atomicExch(&ws.img_total[b], running + 1); // publish
+        }
+    }
+    // chained scan: sum of the totals of images 0..b-1
+    int part = 0;
+    for (int p = tid; p < b; p += FINISH_NT) {
+        int v;
+        while ((v = atomicAdd(&ws.img_total[p], 0)) == 0) __nanosleep(40);
+        part += v - 1;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) s_red[wid] = part;
+    __syncthreads();
+    if (tid == 0) {
+        int base = 0;
+        for (int w = 0; w < FINISH_NT / 32; ++w) base += s_red[w];
+        s_base = base;
+        out_counts[b] = s_total;
+        out_offsets[b] = base;
+        if (b == bs - 1) out_offsets[bs] = base + s_total;
+    }
+    __syncthreads(); // also makes warp 0's kept_off writes visible to the block
+    const int img_base = s_base;
+    if (s_total == 0) return;
+
     double off[2] = {0, 0}, scl[2] = {1, 1}, ims[2] = {1, 1};
     if (cp.enabled) {
         const int *hw = cp.image_hw + (size_t)b * cp.image_hw_stride;
@@ -353,8 +441,11 @@ __global__ void __launch_bounds__(128) gather_kernel(int rows, int nc, NmsWs ws,
             }
         }
     }
-    for (int k = lane; k < nk; k += 32) {
-        const int row = kept_row[k];
+    const size_t ib = (size_t)b * rows;
+    const int total = s_total;
+    // one thread per output row: class found by binary search over the kept offsets (flat mode), or one warp per
+    // class when the class table does not fit shared memory
+    auto write_row = [&](int c, int row, size_t oidx) {
         const float4 bx = ws.box[ib + row];
         const float2 oc = ws.oc[ib + row];
         float o0 = bx.x, o1 = bx.y, o2 = bx.z, o3 = bx.w;
@@ -379,10 +470,29 @@ __global__ void __launch_bounds__(128) gather_kernel(int rows, int nc, NmsWs ws,
             }
             o0 = mn[0]; o1 = mn[1]; o2 = mx[0]; o3 = mx[1];
         }
-        float *o = out_rows + (obase + k) * 7;
+        float *o = out_rows + oidx * 7;
         o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
         o[4] = oc.x; o[5] = oc.y; o[6] = (float)c;
-        out_idx[obase + k] = row;
+        out_idx[oidx] = row;
+    };
+    if (flat) {
+        for (int k = tid; k < total; k += FINISH_NT) {
+            int lo = 0, hi = nc; // last c with s_koff[c] <= k (empty classes share their successor's offset)
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_koff[mid] <= k) lo = mid;
+                else hi = mid;
+            }
+            write_row(lo, ws.kept_row[ib + s_soff[lo] + (k - s_koff[lo])], (size_t)img_base + k);
+        }
+    } else {
+        for (int c = wid; c < nc; c += FINISH_NT / 32) {
+            const int nk = ws.kept_count[sb + c];
+            if (nk == 0) continue;
+            const int *kept_row = ws.kept_row + ib + ws.seg_off[sb + c];
+            const size_t obase = (size_t)img_base + ws.kept_off[sb + c];
+            for (int k = lane; k < nk; k += 32) write_row(c, kept_row[k], obase + k);
+        }
     }
 }
 
@@ -413,13 +523,11 @@ static float thr_to_f32_floor(double thr)
 int launch_nms_tail(const yc_nms_params *p, const NmsWs &ws, float *out_rows, int *out_idx, int *out_counts,
                     int *out_offsets, cudaStream_t stream)
 {
-    segment_offsets_kernel<<<p->bs, 256, 0, stream>>>(p->nc, ws);
-    bucket_scatter_kernel<<<dim3((p->rows + 255) / 256, p->bs), 256, 0, stream>>>(p->rows, p->nc, ws);
-    nms_segment_kernel<<<dim3(p->nc, p->bs), NMS_NT, 0, stream>>>(p->rows, p->nc, thr_to_f32_floor(p->nms_thres), ws);
-    kept_scan_kernel<<<1, 1024, 0, stream>>>(p->bs, p->nc, ws, out_counts, out_offsets);
+    bucket_kernel<<<dim3((p->rows + BUCKET_SLOTS - 1) / BUCKET_SLOTS, p->bs), 256, 0, stream>>>(p->rows, p->nc, ws);
+    nms_segment_kernel<<<dim3((p->nc + NMS_NT / 32 - 1) / (NMS_NT / 32), p->bs), NMS_NT, 0, stream>>>(
+        p->rows, p->nc, thr_to_f32_floor(p->nms_thres), ws);
     CorrectParams cp{p->correct_boxes, p->letterbox, p->input_h, p->input_w, (const int *)p->image_hw, p->image_hw_stride};
-    gather_kernel<<<dim3((p->nc + 3) / 4, p->bs), 128, 0, stream>>>(p->rows, p->nc, ws, out_offsets, out_rows, out_idx,
-                                                                    cp);
+    finish_kernel<<<p->bs, FINISH_NT, 0, stream>>>(p->bs, p->rows, p->nc, ws, out_counts, out_offsets, out_rows, out_idx, cp);
     YC_CUDA(cudaGetLastError());
     return YC_OK;
 }

@@ -79,10 +79,11 @@ class PostBackbone:
         p.image_hw, p.image_hw_stride = self.image_hw.data_ptr(), (2 if hw.shape[0] > 1 else 0)
         p.box_div_w, p.box_div_h = float(input_shape[1]), float(input_shape[0])
         self.nms_params = p
-        # fused mode: one head kernel whose epilogue emits the NMS candidates (z never written) + 5 NMS kernels;
-        # otherwise head kernel (writes z) + threshold/compaction + the same 5.  (memsets are not kernels)
+        # fused mode: one head kernel whose epilogue emits the NMS candidates (z never written) + 3 NMS kernels
+        # (bucket, per-segment NMS, finish); otherwise head kernel (writes z) + threshold/compaction + the same 3.
+        # (memsets are not kernels)
         self.fused = fused and dtype == torch.bfloat16
-        self.kernels_per_step = 6 if self.fused else 7
+        self.kernels_per_step = 4 if self.fused else 5
         self._graphs = {}
         self.use_graph = use_graph
 
@@ -113,7 +114,7 @@ class PostBackbone:
             if rc != _lib.YC_ERR_UNSUPPORTED:
                 _lib.check(rc, "yc_detect_fused")
                 return
-            self.fused, self.kernels_per_step = False, 7   # shape does not fit the tcgen05 kernel: two-call path
+            self.fused, self.kernels_per_step = False, 5   # shape does not fit the tcgen05 kernel: two-call path
         _lib.check(_lib.lib.yc_head_forward(C.byref(self.desc), s), "yc_head_forward")
         _lib.check(_lib.lib.yc_nms_batched(self.z.data_ptr(), C.byref(self.nms_params), self.ws.data_ptr(),
                                            self.ws.numel(), self.out_rows.data_ptr(), self.out_idx.data_ptr(),
