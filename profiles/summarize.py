@@ -22,7 +22,7 @@ def launches(path):
     for r in rows[hdr + 1:]:
         if len(r) > vi:
             agg.setdefault(r[ki], []).append(float(r[vi].replace(",", "")))
-    mine = {k: v for k, v in agg.items() if k.startswith("yc::") and "pack" not in k}
+    mine = {k: v for k, v in agg.items() if "yc::" in k and "pack" not in k}
     tot = sum(sum(v) / len(v) for v in mine.values())
     print(f"{'kernel':72s} {'n':>4s} {'avg us':>9s} {'share':>7s}")
     for k, v in agg.items():

@@ -272,13 +272,17 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             // thread is unaware: it reads B from the slot as usual; a slot's B half is only ever written
             // by this thread, after the slot's empty barrier).
             int resident_lv = -1;
+            const bool prof = (P.debug & 8) && blockIdx.x == 0;
+            long long p_wait = 0, p_t0 = clock64();
             for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
                 const TileCoord tc = tile_coord(P, t);
                 const int nkb = (P.lv[tc.lv].K + TC_BK - 1) / TC_BK;
                 const bool aligned = nkb == n_stages && stage == 0;
                 const bool load_b = !(aligned && resident_lv == tc.lv);
                 for (int kb = 0; kb < nkb; ++kb) {
+                    const long long w0 = prof ? clock64() : 0;
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (prof) p_wait += clock64() - w0;
                     uint8_t *sa = stage_base + stage * TC_STAGE_BYTES, *sb = sa + TC_A_BYTES;
                     if (P.debug & 4) {
                         mbar_arrive(&full_bar[stage]);
@@ -297,6 +301,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 }
                 resident_lv = aligned ? tc.lv : -1;
             }
+            if (prof) printf("[yc prof] producer: total %lld cyc, waiting on empty %lld\n", clock64() - p_t0, p_wait);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one elected lane) =====================
@@ -304,15 +309,22 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            const bool prof = (P.debug & 8) && blockIdx.x == 0;
+            long long m_wt = 0, m_wf = 0, m_t0 = clock64();
+            int m_kb = 0;
             for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
                 const TileCoord tc = tile_coord(P, t);
                 const int nkb = (P.lv[tc.lv].K + TC_BK - 1) / TC_BK;
                 const int buf = it & 1;
+                long long w0 = prof ? clock64() : 0;
                 mbar_wait(&tempty_bar[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u); // epilogue drained this buffer
+                if (prof) m_wt += clock64() - w0;
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_MAX_N;
                 for (int kb = 0; kb < nkb; ++kb) {
+                    w0 = prof ? clock64() : 0;
                     mbar_wait(&full_bar[stage], phase);
+                    if (prof) { m_wf += clock64() - w0; ++m_kb; }
                     tc_fence_after();
                     const uint32_t sa = smem_addr(stage_base + stage * TC_STAGE_BYTES), sb = sa + TC_A_BYTES;
 #pragma unroll
@@ -330,6 +342,9 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (prof)
+                printf("[yc prof] mma: total %lld cyc, %d tiles %d k-blocks, waiting on tmem-empty %lld, on smem-full %lld\n",
+                       clock64() - m_t0, it, m_kb, m_wt, m_wf);
         }
     } else if (warp >= TC_NON_EPI_THREADS / 32) {
         // ===================== epilogue: TMEM -> sigmoid/decode -> slab -> bulk store =====================

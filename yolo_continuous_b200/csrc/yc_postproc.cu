@@ -324,17 +324,18 @@ __device__ __forceinline__ void nms_segment_warp(int b, int c, int n, int rows, 
     if (lane == 0) ws.kept_count[seg] = __popc(mask);
 }
 
-// grid (ceil(nc / 4), bs), 4 warps: warp w owns class blockIdx.x*4 + w.  Segments of up to 32 boxes (the
+// grid (ceil(nc / spc), bs), 4 warps: warp w < spc owns class blockIdx.x*spc + w (spc = 4 when there are many
+// segments, 1 when the grid would otherwise not fill the GPU).  Segments of up to 32 boxes (the
 // common case at detection thresholds) are finished by their warp; larger ones are then processed one
 // after another by the whole CTA.
-__global__ void __launch_bounds__(NMS_NT) nms_segment_kernel(int rows, int nc, float thr_f, NmsWs ws)
+__global__ void __launch_bounds__(NMS_NT) nms_segment_kernel(int rows, int nc, float thr_f, int spc, NmsWs ws)
 {
     __shared__ NmsSmem sm;
     __shared__ int big_n[NMS_NT / 32];
     const int b = blockIdx.y, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * (NMS_NT / 32) + wid;
+    const int c = blockIdx.x * spc + wid; // spc = segments (warps in use) per CTA: 4, or 1 for small grids
     int n = 0;
-    if (c < nc) n = ws.hist[(size_t)b * nc + c];
+    if (wid < spc && c < nc) n = ws.hist[(size_t)b * nc + c];
     if (n == 1) {
         if (lane == 0) {
             const size_t ib = (size_t)b * rows;
@@ -347,9 +348,9 @@ __global__ void __launch_bounds__(NMS_NT) nms_segment_kernel(int rows, int nc, f
     }
     if (lane == 0) big_n[wid] = n > 32 ? n : 0;
     __syncthreads();
-    for (int w = 0; w < NMS_NT / 32; ++w) {
+    for (int w = 0; w < spc; ++w) {
         const int nb = big_n[w]; // uniform across the CTA
-        if (nb) nms_segment_cta(b, blockIdx.x * (NMS_NT / 32) + w, nb, rows, nc, thr_f, ws, sm);
+        if (nb) nms_segment_cta(b, blockIdx.x * spc + w, nb, rows, nc, thr_f, ws, sm);
     }
 }
 
@@ -367,7 +368,7 @@ struct CorrectParams {
     int image_hw_stride;
 };
 
-constexpr int FINISH_NT = 128;
+constexpr int FINISH_NT = 512;
 constexpr int FINISH_SMEM_NC = 1024;
 
 __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int nc, NmsWs ws, int *__restrict__ out_counts,
@@ -524,8 +525,9 @@ int launch_nms_tail(const yc_nms_params *p, const NmsWs &ws, float *out_rows, in
                     int *out_offsets, cudaStream_t stream)
 {
     bucket_kernel<<<dim3((p->rows + BUCKET_SLOTS - 1) / BUCKET_SLOTS, p->bs), 256, 0, stream>>>(p->rows, p->nc, ws);
-    nms_segment_kernel<<<dim3((p->nc + NMS_NT / 32 - 1) / (NMS_NT / 32), p->bs), NMS_NT, 0, stream>>>(
-        p->rows, p->nc, thr_to_f32_floor(p->nms_thres), ws);
+    const int spc = (long long)p->nc * p->bs >= 8 * 148 ? NMS_NT / 32 : 1;
+    nms_segment_kernel<<<dim3((p->nc + spc - 1) / spc, p->bs), NMS_NT, 0, stream>>>(p->rows, p->nc,
+                                                                                     thr_to_f32_floor(p->nms_thres), spc, ws);
     CorrectParams cp{p->correct_boxes, p->letterbox, p->input_h, p->input_w, (const int *)p->image_hw, p->image_hw_stride};
     finish_kernel<<<p->bs, FINISH_NT, 0, stream>>>(p->bs, p->rows, p->nc, ws, out_counts, out_offsets, out_rows, out_idx, cp);
     YC_CUDA(cudaGetLastError());
@@ -587,7 +589,7 @@ extern "C" int yc_nms_single(const float *boxes, const float *scores, int n, dou
                "yc_nms_single: workspace %zu < %zu", workspace_bytes, ws.total_bytes + 256);
     YC_CUDA(cudaMemsetAsync(ws.counters, 0, ws.counters_bytes, stream));
     single_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(boxes, scores, n, ws);
-    nms_segment_kernel<<<dim3(1, 1), NMS_NT, 0, stream>>>(n, 1, thr_to_f32_floor(thr), ws);
+    nms_segment_kernel<<<dim3(1, 1), NMS_NT, 0, stream>>>(n, 1, thr_to_f32_floor(thr), 1, ws);
     single_finish_kernel<<<min((n + 255) / 256, 64), 256, 0, stream>>>(ws, keep, keep_count_dev);
     YC_CUDA(cudaGetLastError());
     return YC_OK;
