@@ -44,6 +44,9 @@ constexpr int TC_NON_EPI_THREADS = 128;
 struct TcLevel {
     const float2 *sb;   // (scale, bias2) per column
     float *raw;         // [bs, na, HW, no] or null
+    int n_groups;       // anchor groups per pixel tile: 1 (all anchors in one 256-column MMA tile) or na (IBin: one
+                        // 128-column MMA tile per anchor); tiles of a level are ordered pixel-block major, group minor
+    int bmap0;          // first weight tensor map of this level (one per group)
     int K, HW, nx;
     int tiles_per_img;  // ceil(HW / 128)
     int tile_begin;     // first tile id of this level in schedule order
@@ -56,7 +59,12 @@ struct TcParams {
     TcLevel lv[YC_MAX_LEVELS]; // in schedule order (largest K first)
     int n_lv;
     int total_tiles;
-    int bs, na, no, npad;
+    int bs, na, no, npad;      // na = anchors per MMA tile (epilogue warp groups), no = accumulator columns per anchor
+    int na_real;               // anchors of the head (raw map indexing)
+    int no_out;                // columns of a z row (no; IBin: nc + 5)
+    int ibin, bin_count;       // IBin decode (nets/ibin.py:56-72)
+    float bin_step;
+    const float *bins;         // device [bin_count] (SigmoidBin.bins)
     int rows_total;
     int write_z;               // 0 for YC_HEAD_RAW
     float *z;
@@ -74,10 +82,10 @@ struct TcParams {
 
 struct TcMaps {
     CUtensorMap a[YC_MAX_LEVELS];
-    CUtensorMap b[YC_MAX_LEVELS];
+    CUtensorMap b[YC_MAX_LEVELS * YC_MAX_ANCHORS];
 };
 
-struct TileCoord { int lv, b, p0; };
+struct TileCoord { int lv, b, p0, g; };
 
 __device__ __forceinline__ TileCoord tile_coord(const TcParams &P, int t)
 {
@@ -85,9 +93,11 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams &P, int t)
 #pragma unroll
     for (int i = 1; i < YC_MAX_LEVELS; ++i)
         if (i < P.n_lv && t >= P.lv[i].tile_begin) l = i;
-    const int r = t - P.lv[l].tile_begin;
+    int r = t - P.lv[l].tile_begin;
     TileCoord c;
     c.lv = l;
+    c.g = 0;
+    if (P.lv[l].n_groups > 1) { c.g = r % P.lv[l].n_groups; r /= P.lv[l].n_groups; }
     c.b = r / P.lv[l].tiles_per_img;
     c.p0 = (r - c.b * P.lv[l].tiles_per_img) * TC_BM;
     return c;
@@ -133,6 +143,65 @@ __device__ __forceinline__ void epi_row(uint32_t taddr, int no, const float2 *__
     if (rem & 4) { epi_chunk<4, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 4; }
     if (rem & 2) { epi_chunk<2, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 2; }
     if (rem & 1) { epi_chunk<1, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); }
+}
+
+
+// IBin z row (reference nets/ibin.py:56-72, losses/sigmoid_bin.py:49-63) from the 127 accumulator columns of one
+// (pixel, anchor): [x, y | w: reg + bins | h: reg + bins | obj | cls] -> [x, y, w, h, obj, cls]; argmax over the
+// sigmoided bins takes the first maximum.  Same operation order as ibin_decode_kernel (generic path).
+template <int W>
+__device__ __forceinline__ void ibin_chunk(uint32_t taddr, int c0, const float2 *__restrict__ sb, float *__restrict__ srow,
+                                           float gx, float gy, float stride, int len, float &reg_w, float &reg_h, float &best_w,
+                                           float &best_h, int &idx_w, int &idx_h)
+{
+    uint32_t v[W];
+    TmemLd<W>::ld(taddr + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const int o = c0 + j;
+        const float2 s_b = __ldg(sb + o);
+        const float sg = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
+        if (o < 2) {
+            srow[o] = decode_xy(sg, o == 0 ? gx : gy, stride);
+        } else if (o < 2 + 2 * len) {
+            if (o < 2 + len) {
+                const int k = o - 2;
+                if (k == 0) reg_w = sg;
+                else if (sg > best_w) { best_w = sg; idx_w = k - 1; }
+            } else {
+                const int k = o - 2 - len;
+                if (k == 0) reg_h = sg;
+                else if (sg > best_h) { best_h = sg; idx_h = k - 1; }
+            }
+        } else {
+            srow[o - 2 * len + 2] = sg;
+        }
+    }
+}
+
+__device__ __forceinline__ void epi_row_ibin(uint32_t taddr, int no, const float2 *__restrict__ sb, float *__restrict__ srow,
+                                             float gx, float gy, float stride, float aw, float ah, const TcParams &P)
+{
+    const int len = P.bin_count + 1;
+    float reg_w = 0.f, reg_h = 0.f, best_w = -1.f, best_h = -1.f;
+    int idx_w = 0, idx_h = 0;
+    int c0 = 0;
+    for (; c0 + 16 <= no; c0 += 16) ibin_chunk<16>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h);
+    const int rem = no - c0;
+    if (rem & 8) { ibin_chunk<8>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 8; }
+    if (rem & 4) { ibin_chunk<4>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 4; }
+    if (rem & 2) { ibin_chunk<2>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 2; }
+    if (rem & 1) { ibin_chunk<1>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); }
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        float r = __fmul_rn(d == 0 ? reg_w : reg_h, 2.0f);
+        r = __fadd_rn(r, -1.0f);
+        r = __fmul_rn(r, P.bin_step);
+        float res = __fadd_rn(r, __ldg(P.bins + (d == 0 ? idx_w : idx_h)));
+        res = fminf(fmaxf(res, 0.0f), 4.0f);
+        srow[2 + d] = __fmul_rn(res, d == 0 ? aw : ah);
+    }
 }
 
 
@@ -238,7 +307,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < P.n_lv; ++i) {
             prefetch_tmap(&maps.a[i]);
-            prefetch_tmap(&maps.b[i]);
+            for (int g = 0; g < P.lv[i].n_groups; ++g) prefetch_tmap(&maps.b[P.lv[i].bmap0 + g]);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -278,7 +347,8 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 const TileCoord tc = tile_coord(P, t);
                 const int nkb = (P.lv[tc.lv].K + TC_BK - 1) / TC_BK;
                 const bool aligned = nkb == n_stages && stage == 0;
-                const bool load_b = !(aligned && resident_lv == tc.lv);
+                const int wkey = tc.lv * YC_MAX_ANCHORS + tc.g; // identifies the weight tile
+                const bool load_b = !(aligned && resident_lv == wkey);
                 for (int kb = 0; kb < nkb; ++kb) {
                     const long long w0 = prof ? clock64() : 0;
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -294,12 +364,13 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         if (load_b) {
 #pragma unroll
                             for (int j = 0; j < BK / 64; ++j)
-                                tma_load_2d(sb + j * TC_B_BOX_BYTES, &maps.b[tc.lv], &full_bar[stage], kb * TC_BK + j * 64, 0);
+                                tma_load_2d(sb + j * TC_B_BOX_BYTES, &maps.b[P.lv[tc.lv].bmap0 + tc.g], &full_bar[stage],
+                                            kb * TC_BK + j * 64, 0);
                         }
                     }
                     if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                 }
-                resident_lv = aligned ? tc.lv : -1;
+                resident_lv = aligned ? wkey : -1;
             }
             if (prof) printf("[yc prof] producer: total %lld cyc, waiting on empty %lld\n", clock64() - p_t0, p_wait);
         }
@@ -352,8 +423,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int q = warp & 3;     // TMEM lane quadrant this warp may read
         const int a = e >> 2;       // anchor handled by this warp
         float *slab = (float *)((uint8_t *)slabs + (size_t)e * P.slab_bytes);
-        float *srow = slab + lane * P.no;
-        const int no = P.no;
+        const int no = P.no, no_out = P.no_out;
         int it = 0;
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
             const TileCoord tc = tile_coord(P, t);
@@ -363,8 +433,9 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const int nv = min(32, L.HW - prow0);        // valid rows (<= 0: nothing to store)
             const int p = prow0 + lane;
             const float gx = (float)(p % L.nx), gy = (float)(p / L.nx);
-            const float aw = L.anchor_wh[2 * a], ah = L.anchor_wh[2 * a + 1];
-            const float2 *sb = L.sb + a * no;
+            const int ar = tc.g * P.na + a;               // anchor of the head this warp decodes
+            const float aw = L.anchor_wh[2 * ar], ah = L.anchor_wh[2 * ar + 1];
+            const float2 *sb = L.sb + ar * no;
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_MAX_N + a * no);
 
             mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
@@ -435,7 +506,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                             const float bw = decode_wh(sigmoidf_fast(t2), aw), bh = decode_wh(sigmoidf_fast(t3), ah);
                             float x1, y1, x2, y2;
                             xywh_to_corners(cx, cy, bw, bh, P.div_w, P.div_h, x1, y1, x2, y2);
-                            emit_one(tc.b, L.row_off + a * L.HW + ps, P.rows_total, nc, x1, y1, x2, y2, o_s, bv, score, best,
+                            emit_one(tc.b, L.row_off + ar * L.HW + ps, P.rows_total, nc, x1, y1, x2, y2, o_s, bv, score, best,
                                      P.ws);
                         }
                     }
@@ -454,7 +525,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     const float bw = decode_wh(sigmoidf_fast(tb[2]), aw), bh = decode_wh(sigmoidf_fast(tb[3]), ah);
                     float x1, y1, x2, y2;
                     xywh_to_corners(cx, cy, bw, bh, P.div_w, P.div_h, x1, y1, x2, y2);
-                    emit_candidates(pass, tc.b, L.row_off + a * L.HW + p, P.rows_total, P.nc, x1, y1, x2, y2, obj, bv,
+                    emit_candidates(pass, tc.b, L.row_off + ar * L.HW + p, P.rows_total, P.nc, x1, y1, x2, y2, obj, bv,
                                     score, best, P.ws);
                 }
                 tc_fence_before();
@@ -465,22 +536,23 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (L.raw) {
                 if (lane == 0) bulk_wait_read0(); // previous store from this slab has been read out
                 __syncwarp();
-                epi_row<true>(taddr, no, sb, srow, gx, gy, L.stride, aw, ah);
+                epi_row<true>(taddr, no, sb, slab + lane * no, gx, gy, L.stride, aw, ah);
                 if (nv > 0)
-                    slab_store(L.raw + (((size_t)tc.b * P.na + a) * L.HW + prow0) * no, slab, nv, no, lane);
+                    slab_store(L.raw + (((size_t)tc.b * P.na_real + ar) * L.HW + prow0) * no, slab, nv, no, lane);
             }
             if (P.write_z) {
                 if (lane == 0) bulk_wait_read0();
                 __syncwarp();
-                epi_row<false>(taddr, no, sb, srow, gx, gy, L.stride, aw, ah);
+                if (P.ibin) epi_row_ibin(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, aw, ah, P);
+                else epi_row<false>(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, aw, ah);
             }
             // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
             if (P.write_z && nv > 0)
-                slab_store(P.z + ((size_t)tc.b * P.rows_total + L.row_off + (size_t)a * L.HW + prow0) * no, slab, nv, no,
-                           lane);
+                slab_store(P.z + ((size_t)tc.b * P.rows_total + L.row_off + (size_t)ar * L.HW + prow0) * no_out, slab, nv,
+                           no_out, lane);
         }
         if (lane == 0) bulk_wait_all0(); // global writes complete before the CTA exits
     }
@@ -515,16 +587,23 @@ static int g_num_sms = 0;
 int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, unsigned *left_mask,
                         const FusedDetect *fused, cudaStream_t stream)
 {
-    const int N = d->na * d->no, npad = round_up(N, 16);
+    const int N = d->na * d->no;
+    // MMA tile: all anchors side by side when they fit 256 accumulator columns (IDetect: 3 x 85), otherwise one
+    // anchor per tile (IBin: 127 -> 128 columns), the anchors of a pixel block being consecutive tiles
+    const bool ibin = d->kind == YC_HEAD_IBIN;
+    const int na_tile = (!ibin && round_up(N, 16) <= TC_MAX_N) ? d->na : 1;
+    const int n_groups = d->na / na_tile;
+    const int npad = round_up(na_tile * d->no, 16);
+    const int npad_total = round_up(N, 16);
     YC_REQUIRE(d->x_dtype == YC_BF16, YC_ERR_UNSUPPORTED, "tcgen05 head: feature maps must be bf16 (fp32 maps use the exact FFMA path)");
-    YC_REQUIRE(d->kind == YC_HEAD_IDETECT || d->kind == YC_HEAD_RAW, YC_ERR_UNSUPPORTED,
-               "tcgen05 head: kind %d not supported yet", d->kind);
-    YC_REQUIRE(npad <= TC_MAX_N && d->na <= 3, YC_ERR_UNSUPPORTED, "tcgen05 head: na*no=%d (na=%d) exceeds one 256-column tile",
-               N, d->na);
+    YC_REQUIRE(!(fused && ibin), YC_ERR_UNSUPPORTED, "tcgen05 head: the fused step supports IDetect-style decode only");
+    YC_REQUIRE(npad <= TC_MAX_N && na_tile <= 3, YC_ERR_UNSUPPORTED,
+               "tcgen05 head: %d anchors x %d outputs do not fit the 256-column accumulator tile", d->na, d->no);
     EncodeTiledFn enc = encode_tiled();
     YC_REQUIRE(enc != nullptr, YC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
 
     // per epilogue warp: z slab (32 rows) or, in the fused mode, the survivor queue (TC_QUEUE_ROWS x nc floats)
+    const int no_out = ibin ? d->no - 2 * (d->bin_count + 1) + 2 : d->no;
     const uint32_t slab_bytes = fused ? (uint32_t)round_up(TC_QUEUE_ROWS * (d->no - 5) * 4, 16)
                                       : (uint32_t)round_up(32 * d->no * 4, 16);
     // K=64 per stage: 4 stages in the fused mode (no z slabs in shared memory), 2 next to the slabs.
@@ -532,7 +611,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     int bk = 64;
     { const char *e = getenv("YC_TC_BK"); if (e && (atoi(e) == 64 || atoi(e) == 128)) bk = atoi(e); }
     const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * TC_B_BOX_BYTES;
-    const size_t fixed = 1024 + (size_t)4 * d->na * slab_bytes + 256;
+    const size_t fixed = 1024 + (size_t)4 * na_tile * slab_bytes + 256;
     int stages = TC_MAX_STAGES;
     while (stages > 2 && fixed + (size_t)stages * stage_bytes > 227 * 1024) --stages;
     const size_t smem_bytes = fixed + (size_t)stages * stage_bytes;
@@ -562,9 +641,15 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     TcParams P;
     memset(&P, 0, sizeof(P));
     P.n_lv = n;
-    P.bs = d->bs; P.na = d->na; P.no = d->no; P.npad = npad;
+    P.bs = d->bs; P.na = na_tile; P.no = d->no; P.npad = npad;
+    P.na_real = d->na; P.no_out = no_out;
     P.rows_total = rows_total;
-    P.write_z = d->kind == YC_HEAD_IDETECT ? 1 : 0;
+    P.write_z = d->kind != YC_HEAD_RAW ? 1 : 0;
+    if (ibin) {
+        P.ibin = 1; P.bin_count = d->bin_count;
+        P.bin_step = (float)(4.0 / (double)d->bin_count); // SigmoidBin(min=0, max=4), nets/ibin.py:16-17
+        P.bins = d->bins;
+    }
     P.z = d->z;
     P.idesc = instr_desc_f16(/*bf16*/ 1, /*A MN-major*/ 1, /*B K-major*/ 0, TC_BM, (uint32_t)npad);
     P.b_box_bytes = (uint32_t)npad * 64 * 2;
@@ -587,11 +672,13 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         L.raw = lv.raw;
         L.K = lv.K; L.HW = HW; L.nx = lv.W;
         L.tiles_per_img = (HW + TC_BM - 1) / TC_BM;
+        L.n_groups = n_groups;
+        L.bmap0 = s * n_groups;
         L.tile_begin = tiles;
         L.row_off = row_off[i];
         L.stride = lv.stride;
         for (int j = 0; j < YC_MAX_ANCHORS * 2; ++j) L.anchor_wh[j] = lv.anchor_wh[j];
-        tiles += d->bs * L.tiles_per_img;
+        tiles += d->bs * L.tiles_per_img * n_groups;
         {   // A: X [bs, K, HW] bf16, box {64 px, 64 k, 1}
             cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)lv.K, (cuuint64_t)d->bs};
             cuuint64_t gstr[2] = {(cuuint64_t)HW * 2, (cuuint64_t)HW * lv.K * 2};
@@ -601,12 +688,14 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             YC_REQUIRE(r == CUDA_SUCCESS, YC_ERR_CUDA, "cuTensorMapEncodeTiled(A, level %d) failed: %d", i, (int)r);
         }
-        {   // B: W [Npad, K] bf16, box {64 k, Npad}
-            cuuint64_t gdim[2] = {(cuuint64_t)lv.K, (cuuint64_t)npad};
+        for (int g = 0; g < n_groups; ++g) {   // B: rows [g*na_tile*no, ...) of W [Npad_total, K] bf16, box {64 k, npad}
+            const int row0 = g * na_tile * d->no;  // rows past Npad_total are zero-filled by TMA
+            cuuint64_t gdim[2] = {(cuuint64_t)lv.K, (cuuint64_t)(npad_total - row0)};
             cuuint64_t gstr[1] = {(cuuint64_t)lv.K * 2};
             cuuint32_t box[2] = {64, (cuuint32_t)npad}, est[2] = {1, 1};
-            CUresult r = enc(&maps.b[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)bv.w_bf, gdim, gstr, box, est,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CUresult r = enc(&maps.b[s * n_groups + g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                             (void *)(bv.w_bf + (size_t)row0 * lv.K), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             YC_REQUIRE(r == CUDA_SUCCESS, YC_ERR_CUDA, "cuTensorMapEncodeTiled(B, level %d) failed: %d", i, (int)r);
         }
@@ -619,7 +708,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         YC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    const int threads = TC_NON_EPI_THREADS + 128 * d->na;
+    const int threads = TC_NON_EPI_THREADS + 128 * na_tile;
     if (bk == 128) {
         YC_CUDA(cudaFuncSetAttribute(head_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         head_tc_kernel<128><<<grid, threads, smem_bytes, stream>>>(maps, P);
