@@ -10,8 +10,8 @@ namespace yc {
 
 constexpr int TC_ROWS = 128;    // rows per CTA in the threshold/compaction kernel
 constexpr int NMS_NT = 128;     // threads per NMS CTA == sorted boxes per chunk
-constexpr int SORT_SMEM = 2048; // segments up to this size are sorted in shared memory
-constexpr int KEPT_SMEM = 512;  // kept boxes cached in shared memory per segment
+constexpr int SORT_SMEM = 1024; // segments up to this size are sorted in shared memory
+constexpr int KEPT_SMEM = 256;  // kept boxes cached in shared memory per segment
 
 // ---- mbarrier / bulk-copy helpers (TMA 1D) -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -179,6 +179,8 @@ struct NmsSmem {
     float4 skept[KEPT_SMEM];
     unsigned long long smask[NMS_NT][2];
     unsigned int sdead[NMS_NT / 32];
+    unsigned int sany[NMS_NT / 32];
+    unsigned long long skeptw[2];
     int s_nkept;
 };
 
@@ -188,7 +190,8 @@ __device__ void nms_segment_cta(int b, int c, int n, int rows, int nc, float thr
     unsigned long long *skeys = sm.skeys;
     float4 *sbox = sm.sbox, *skept = sm.skept;
     unsigned long long(*smask)[2] = sm.smask;
-    unsigned int *sdead = sm.sdead;
+    unsigned int *sdead = sm.sdead, *sany = sm.sany;
+    unsigned long long *skeptw = sm.skeptw;
     int &s_nkept = sm.s_nkept;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t seg = (size_t)b * nc + c;
@@ -257,31 +260,45 @@ __device__ void nms_segment_cta(int b, int c, int n, int rows, int nc, float thr
         smask[tid][0] = m0;
         smask[tid][1] = m1;
         const unsigned d = __ballot_sync(0xffffffffu, dead);
-        if (lane == 0) sdead[wid] = d;
+        const unsigned any_mask = __ballot_sync(0xffffffffu, (m0 | m1) != 0ull);
+        if (lane == 0) { sdead[wid] = d; sany[wid] = any_mask; }
         __syncthreads();
+        // kept set of this chunk as a 128-bit map (keptw): without intra-chunk overlaps it is simply the boxes
+        // that survived the kept-list test; otherwise warp 0 walks the bitmask (greedy rule, in score order)
         if (wid == 0) {
             unsigned long long remv = 0;
             if (lane < 2) remv = (unsigned long long)sdead[2 * lane] | ((unsigned long long)sdead[2 * lane + 1] << 32);
-            int cnt = nk;
-            for (int w = 0; w < 2; ++w) {
-                while (true) {
-                    const unsigned long long cur = __shfl_sync(0xffffffffu, remv, w);
-                    const unsigned long long alive = ~cur;
-                    if (!alive) break;
-                    const int i = __ffsll((long long)alive) - 1;
-                    const int idx = w * 64 + i;
-                    if (lane < 2) remv |= smask[idx][lane];
-                    if (lane == w) remv |= 1ull << i;
-                    if (lane == 0) {
-                        const float4 kb = sbox[idx];
-                        kept_row[cnt] = (int)(K[base + idx] & 0xffffffffull);
-                        if (cnt < KEPT_SMEM) skept[cnt] = kb;
-                        else kept_box[cnt] = kb;
+            unsigned long long kept = 0;
+            const bool overlaps = (sany[0] | sany[1] | sany[2] | sany[3]) != 0u;
+            if (!overlaps) {
+                kept = ~remv;
+            } else {
+                for (int w = 0; w < 2; ++w) {
+                    while (true) {
+                        const unsigned long long cur = __shfl_sync(0xffffffffu, remv, w);
+                        const unsigned long long alive = ~cur;
+                        if (!alive) break;
+                        const int i = __ffsll((long long)alive) - 1;
+                        if (lane < 2) remv |= smask[w * 64 + i][lane];
+                        if (lane == w) { remv |= 1ull << i; kept |= 1ull << i; }
                     }
-                    ++cnt;
                 }
             }
-            if (lane == 0) s_nkept = cnt;
+            if (lane < 2) skeptw[lane] = kept;
+        }
+        __syncthreads();
+        {   // every thread appends its own box if kept: position = kept so far + kept boxes before it in the chunk
+            const unsigned long long k0 = skeptw[0], k1 = skeptw[1];
+            const bool mine = tid < 64 ? (k0 >> tid) & 1ull : (k1 >> (tid - 64)) & 1ull;
+            if (mine) {
+                const int before = tid < 64 ? __popcll(k0 & ((1ull << tid) - 1ull))
+                                            : __popcll(k0) + __popcll(k1 & ((1ull << (tid - 64)) - 1ull));
+                const int pos = nk + before;
+                kept_row[pos] = (int)(K[base + tid] & 0xffffffffull);
+                if (pos < KEPT_SMEM) skept[pos] = bx;
+                else kept_box[pos] = bx;
+            }
+            if (tid == 0) s_nkept = nk + __popcll(k0) + __popcll(k1);
         }
         __syncthreads();
     }
