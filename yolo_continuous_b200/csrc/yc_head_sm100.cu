@@ -16,270 +16,10 @@
 // warp 3 idle, then 4 epilogue warps per anchor (warp%4 = TMEM lane quadrant).
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
 // round-robin tile scheduler over all (level, image, 128-pixel block) tiles, heaviest level first.
-#include <stdlib.h>
 
-#include "yc_common.cuh"
-#include "yc_nms.cuh"
-#include "yc_sm100.cuh"
-
-#ifdef YC_EXPERIMENT_NO_SB
-#define YC_SB(p) make_float2(1.0f, 0.0f)
-#else
-#define YC_SB(p) __ldg(p)
-#endif
+#include "yc_head_tc.cuh"
 
 namespace yc {
-
-using namespace sm100;
-
-constexpr int TC_BM = 128;       // pixels per tile (UMMA M)
-constexpr int TC_MAX_STAGES = 4;
-constexpr int TC_MAX_N = 256;
-// k per pipeline stage is a template parameter BK (64 or 128):
-//   A stage = two {64 px, BK k} bf16 boxes (BK*128 B each); B stage = BK/64 boxes {64 k, Npad} (32 KB each)
-constexpr int TC_B_BOX_BYTES = TC_MAX_N * 64 * 2;    // 32 KB
-constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_NON_EPI_THREADS = 128;
-
-struct TcLevel {
-    const float2 *sb;   // (scale, bias2) per column
-    float *raw;         // [bs, na, HW, no] or null
-    int n_groups;       // anchor groups per pixel tile: 1 (all anchors in one 256-column MMA tile) or na (IBin: one
-                        // 128-column MMA tile per anchor); tiles of a level are ordered pixel-block major, group minor
-    int bmap0;          // first weight tensor map of this level (one per group)
-    int K, HW, nx;
-    int tiles_per_img;  // ceil(HW / 128)
-    int tile_begin;     // first tile id of this level in schedule order
-    int row_off;        // first z row of this level
-    float stride;
-    float anchor_wh[YC_MAX_ANCHORS * 2];
-};
-
-struct TcParams {
-    TcLevel lv[YC_MAX_LEVELS]; // in schedule order (largest K first)
-    int n_lv;
-    int total_tiles;
-    int bs, na, no, npad;      // na = anchors per MMA tile (epilogue warp groups), no = accumulator columns per anchor
-    int na_real;               // anchors of the head (raw map indexing)
-    int no_out;                // columns of a z row (no; IBin: nc + 5)
-    int ibin, bin_count;       // IBin decode (nets/ibin.py:56-72)
-    float bin_step;
-    const float *bins;         // device [bin_count] (SigmoidBin.bins)
-    int rows_total;
-    int write_z;               // 0 for YC_HEAD_RAW
-    float *z;
-    uint32_t idesc;
-    uint32_t b_box_bytes;      // npad * 64 * 2: bytes one weight box brings
-    uint32_t slab_bytes;       // per epilogue warp: 32*no*4 (z slab) or TC_QUEUE_ROWS*nc*4 (fused survivor queue)
-    int debug;                 // YC_TC_DEBUG bits (timing experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA
-    int stages;                // depth of the smem ring
-    // fused mode (yc_detect_fused): the epilogue thresholds and emits NMS candidates, z is never written
-    int fused;
-    int nc;
-    float conf, div_w, div_h;
-    NmsWs ws;
-};
-
-struct TcMaps {
-    CUtensorMap a[YC_MAX_LEVELS];
-    CUtensorMap b[YC_MAX_LEVELS * YC_MAX_ANCHORS];
-};
-
-struct TileCoord { int lv, b, p0, g; };
-
-__device__ __forceinline__ TileCoord tile_coord(const TcParams &P, int t)
-{
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < YC_MAX_LEVELS; ++i)
-        if (i < P.n_lv && t >= P.lv[i].tile_begin) l = i;
-    int r = t - P.lv[l].tile_begin;
-    TileCoord c;
-    c.lv = l;
-    c.g = 0;
-    if (P.lv[l].n_groups > 1) { c.g = r % P.lv[l].n_groups; r /= P.lv[l].n_groups; }
-    c.b = r / P.lv[l].tiles_per_img;
-    c.p0 = (r - c.b * P.lv[l].tiles_per_img) * TC_BM;
-    return c;
-}
-
-// Epilogue for W consecutive accumulator columns [c0, c0+W) of this thread's row.
-//   RAW:   slab[o] = t                     (pre-sigmoid map, forward()'s list `x`)
-//   !RAW:  slab[o] = decode(sigmoid(t))    (z row; o<2 xy, o<4 wh: nets/idetect.py:40-42)
-template <int W, bool RAW>
-__device__ __forceinline__ void epi_chunk(uint32_t taddr, int c0, const float2 *__restrict__ sb, float *__restrict__ srow,
-                                          float gx, float gy, float stride, float aw, float ah)
-{
-    uint32_t v[W];
-    TmemLd<W>::ld(taddr + (uint32_t)c0, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-        const float2 s_b = __ldg(sb + c0 + j); // same address for the whole warp: one broadcast load
-        const float t = fmaf(__uint_as_float(v[j]), s_b.x, s_b.y);
-        float r;
-        if (RAW) {
-            r = t;
-        } else {
-            r = sigmoidf_fast(t);
-            const int o = c0 + j;
-            if (o == 0) r = decode_xy(r, gx, stride);
-            else if (o == 1) r = decode_xy(r, gy, stride);
-            else if (o == 2) r = decode_wh(r, aw);
-            else if (o == 3) r = decode_wh(r, ah);
-        }
-        srow[c0 + j] = r;
-    }
-}
-
-template <bool RAW>
-__device__ __forceinline__ void epi_row(uint32_t taddr, int no, const float2 *__restrict__ sb, float *__restrict__ srow,
-                                        float gx, float gy, float stride, float aw, float ah)
-{
-    int c0 = 0;
-    for (; c0 + 16 <= no; c0 += 16) epi_chunk<16, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah);
-    const int rem = no - c0;
-    if (rem & 8) { epi_chunk<8, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 8; }
-    if (rem & 4) { epi_chunk<4, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 4; }
-    if (rem & 2) { epi_chunk<2, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 2; }
-    if (rem & 1) { epi_chunk<1, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); }
-}
-
-
-// IBin z row (reference nets/ibin.py:56-72, losses/sigmoid_bin.py:49-63) from the 127 accumulator columns of one
-// (pixel, anchor): [x, y | w: reg + bins | h: reg + bins | obj | cls] -> [x, y, w, h, obj, cls]; argmax over the
-// sigmoided bins takes the first maximum.  Same operation order as ibin_decode_kernel (generic path).
-template <int W>
-__device__ __forceinline__ void ibin_chunk(uint32_t taddr, int c0, const float2 *__restrict__ sb, float *__restrict__ srow,
-                                           float gx, float gy, float stride, int len, float &reg_w, float &reg_h, float &best_w,
-                                           float &best_h, int &idx_w, int &idx_h)
-{
-    uint32_t v[W];
-    TmemLd<W>::ld(taddr + (uint32_t)c0, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-        const int o = c0 + j;
-        const float2 s_b = __ldg(sb + o);
-        const float sg = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
-        if (o < 2) {
-            srow[o] = decode_xy(sg, o == 0 ? gx : gy, stride);
-        } else if (o < 2 + 2 * len) {
-            if (o < 2 + len) {
-                const int k = o - 2;
-                if (k == 0) reg_w = sg;
-                else if (sg > best_w) { best_w = sg; idx_w = k - 1; }
-            } else {
-                const int k = o - 2 - len;
-                if (k == 0) reg_h = sg;
-                else if (sg > best_h) { best_h = sg; idx_h = k - 1; }
-            }
-        } else {
-            srow[o - 2 * len + 2] = sg;
-        }
-    }
-}
-
-__device__ __forceinline__ void epi_row_ibin(uint32_t taddr, int no, const float2 *__restrict__ sb, float *__restrict__ srow,
-                                             float gx, float gy, float stride, float aw, float ah, const TcParams &P)
-{
-    const int len = P.bin_count + 1;
-    float reg_w = 0.f, reg_h = 0.f, best_w = -1.f, best_h = -1.f;
-    int idx_w = 0, idx_h = 0;
-    int c0 = 0;
-    for (; c0 + 16 <= no; c0 += 16) ibin_chunk<16>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h);
-    const int rem = no - c0;
-    if (rem & 8) { ibin_chunk<8>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 8; }
-    if (rem & 4) { ibin_chunk<4>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 4; }
-    if (rem & 2) { ibin_chunk<2>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 2; }
-    if (rem & 1) { ibin_chunk<1>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); }
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-        float r = __fmul_rn(d == 0 ? reg_w : reg_h, 2.0f);
-        r = __fadd_rn(r, -1.0f);
-        r = __fmul_rn(r, P.bin_step);
-        float res = __fadd_rn(r, __ldg(P.bins + (d == 0 ? idx_w : idx_h)));
-        res = fminf(fmaxf(res, 0.0f), 4.0f);
-        srow[2 + d] = __fmul_rn(res, d == 0 ? aw : ah);
-    }
-}
-
-
-// ---- fused epilogue (S3): class max / threshold / candidate emission straight from TMEM -----------------
-// logits of W consecutive class columns starting at accumulator column c (class index c - 5)
-template <int W, bool EXACT>
-__device__ __forceinline__ void cls_chunk(uint32_t taddr, int c, const float2 *__restrict__ sb, float &bestv, int &besti)
-{
-    uint32_t v[W];
-    TmemLd<W>::ld(taddr + (uint32_t)c, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-        const float2 s_b = YC_SB(sb + c + j);
-        float t = fmaf(__uint_as_float(v[j]), s_b.x, s_b.y);
-        if (EXACT) {
-            t = sigmoidf_fast(t); // compare what z would hold (first maximum of the sigmoids, torch.max)
-            if (t > bestv) { bestv = t; besti = c + j - 5; }
-        } else {
-            bestv = fmaxf(bestv, t); // quick pass: only the largest class logit is needed
-        }
-    }
-}
-
-template <bool EXACT>
-__device__ __forceinline__ void cls_scan(uint32_t taddr, int no, const float2 *__restrict__ sb, float &bestv, int &besti)
-{
-    int c = 5;
-    for (; c + 16 <= no; c += 16) cls_chunk<16, EXACT>(taddr, c, sb, bestv, besti);
-    const int rem = no - c;
-    if (rem & 8) { cls_chunk<8, EXACT>(taddr, c, sb, bestv, besti); c += 8; }
-    if (rem & 4) { cls_chunk<4, EXACT>(taddr, c, sb, bestv, besti); c += 4; }
-    if (rem & 2) { cls_chunk<2, EXACT>(taddr, c, sb, bestv, besti); c += 2; }
-    if (rem & 1) { cls_chunk<1, EXACT>(taddr, c, sb, bestv, besti); }
-}
-
-
-// survivors of the objectness filter park their raw class accumulators in the warp's shared-memory queue
-template <int W>
-__device__ __forceinline__ void queue_chunk(uint32_t taddr, int c, bool pass, float *__restrict__ qrow)
-{
-    uint32_t v[W];
-    TmemLd<W>::ld(taddr + (uint32_t)c, v);
-    tmem_ld_wait();
-    if (pass) {
-#pragma unroll
-        for (int j = 0; j < W; ++j) qrow[c - 5 + j] = __uint_as_float(v[j]);
-    }
-}
-
-__device__ __forceinline__ void queue_classes(uint32_t taddr, int no, bool pass, float *__restrict__ qrow)
-{
-    int c = 5;
-    for (; c + 16 <= no; c += 16) queue_chunk<16>(taddr, c, pass, qrow);
-    const int rem = no - c;
-    if (rem & 8) { queue_chunk<8>(taddr, c, pass, qrow); c += 8; }
-    if (rem & 4) { queue_chunk<4>(taddr, c, pass, qrow); c += 4; }
-    if (rem & 2) { queue_chunk<2>(taddr, c, pass, qrow); c += 2; }
-    if (rem & 1) { queue_chunk<1>(taddr, c, pass, qrow); }
-}
-
-constexpr int TC_QUEUE_ROWS = 4; // survivors per warp and tile handled through the queue; more -> in-register scan
-
-// warp-cooperative write of `nv` finished rows from the slab to global memory
-__device__ __forceinline__ void slab_store(float *__restrict__ gdst, const float *__restrict__ slab, int nv, int no, int lane)
-{
-    const uint32_t bytes = (uint32_t)nv * no * 4u;
-    fence_proxy_async_smem();
-    __syncwarp();
-    if ((((uintptr_t)gdst | bytes) & 15u) == 0) {
-        if (lane == 0) {
-            bulk_store(gdst, slab, bytes);
-            bulk_commit();
-        }
-    } else { // unaligned span (odd shapes): plain coalesced stores
-        for (int i = lane; i < nv * no; i += 32) gdst[i] = slab[i];
-    }
-}
 
 template <int BK>
 __global__ void __launch_bounds__(TC_NON_EPI_THREADS + 128 * 3, 1)
@@ -447,90 +187,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 continue;
             }
             if (P.fused) {
-                // box + objectness logits (columns 0..4), then the largest class logit
-                uint32_t v4[4], v1[1];
-                TmemLd<4>::ld(taddr, v4);
-                TmemLd<1>::ld(taddr + 4u, v1);
-                tmem_ld_wait();
-                float tb[5];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 s_b = YC_SB(sb + j);
-                    tb[j] = fmaf(__uint_as_float(v4[j]), s_b.x, s_b.y);
-                }
-                {
-                    const float2 s_b = YC_SB(sb + 4);
-                    tb[4] = fmaf(__uint_as_float(v1[0]), s_b.x, s_b.y);
-                }
-                // Early reject on objectness alone: class scores are sigmoids (<= 1), so obj >= conf is necessary
-                // for obj*cls >= conf.  At detection thresholds >99% of rows stop here after 5 columns; only
-                // warps holding a survivor scan the class columns (exactly as the z path would see them).
-                const float obj = sigmoidf_fast(tb[4]);
-                bool pass = lane < nv && obj >= P.conf;
-                const unsigned surv = __ballot_sync(0xffffffffu, pass);
-                const int n_surv = __popc(surv);
-                if (n_surv > 0 && n_surv <= TC_QUEUE_ROWS) {
-                    // Few survivors (the common case): copy their class accumulators to shared memory, hand the
-                    // TMEM buffer back at once, then scan the classes with the 32 lanes spread over the classes.
-                    float *q = slab; // per-warp queue [TC_QUEUE_ROWS][nc]
-                    const int nc = P.nc;
-                    queue_classes(taddr, no, pass, q + __popc(surv & ((1u << lane) - 1u)) * nc);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-                    unsigned left = surv;
-                    for (int sidx = 0; sidx < n_surv; ++sidx) {
-                        const int src = __ffs(left) - 1;
-                        left &= left - 1;
-                        float bv = -1.0f;
-                        int best = 0;
-                        for (int c = lane; c < nc; c += 32) { // ascending classes per lane: strict > keeps the first
-                            const float2 s_b = __ldg(sb + 5 + c);
-                            const float sg = sigmoidf_fast(fmaf(q[sidx * nc + c], s_b.x, s_b.y));
-                            if (sg > bv) { bv = sg; best = c; }
-                        }
-#pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) { // larger value wins, ties go to the smaller class
-                            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                            const int oi = __shfl_xor_sync(0xffffffffu, best, off);
-                            if (ov > bv || (ov == bv && oi < best)) { bv = ov; best = oi; }
-                        }
-                        const float o_s = __shfl_sync(0xffffffffu, obj, src);
-                        const float t0 = __shfl_sync(0xffffffffu, tb[0], src), t1 = __shfl_sync(0xffffffffu, tb[1], src);
-                        const float t2 = __shfl_sync(0xffffffffu, tb[2], src), t3 = __shfl_sync(0xffffffffu, tb[3], src);
-                        const float score = __fmul_rn(o_s, bv);
-                        if (lane == 0 && score >= P.conf) {
-                            const int ps = prow0 + src;
-                            const float cx = decode_xy(sigmoidf_fast(t0), (float)(ps % L.nx), L.stride);
-                            const float cy = decode_xy(sigmoidf_fast(t1), (float)(ps / L.nx), L.stride);
-                            const float bw = decode_wh(sigmoidf_fast(t2), aw), bh = decode_wh(sigmoidf_fast(t3), ah);
-                            float x1, y1, x2, y2;
-                            xywh_to_corners(cx, cy, bw, bh, P.div_w, P.div_h, x1, y1, x2, y2);
-                            emit_one(tc.b, L.row_off + ar * L.HW + ps, P.rows_total, nc, x1, y1, x2, y2, o_s, bv, score, best,
-                                     P.ws);
-                        }
-                    }
-                    __syncwarp();
-                    continue;
-                }
-                if (n_surv > 0) {
-                    // many survivors (low thresholds): class scan in registers, first maximum of the sigmoids
-                    float bv = -1.0f;
-                    int best = 0;
-                    cls_scan<true>(taddr, no, sb, bv, best);
-                    const float score = __fmul_rn(obj, bv);
-                    pass = pass && score >= P.conf;
-                    const float cx = decode_xy(sigmoidf_fast(tb[0]), gx, L.stride);
-                    const float cy = decode_xy(sigmoidf_fast(tb[1]), gy, L.stride);
-                    const float bw = decode_wh(sigmoidf_fast(tb[2]), aw), bh = decode_wh(sigmoidf_fast(tb[3]), ah);
-                    float x1, y1, x2, y2;
-                    xywh_to_corners(cx, cy, bw, bh, P.div_w, P.div_h, x1, y1, x2, y2);
-                    emit_candidates(pass, tc.b, L.row_off + ar * L.HW + p, P.rows_total, P.nc, x1, y1, x2, y2, obj, bv,
-                                    score, best, P.ws);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane);
                 continue;
             }
             if (L.raw) {
@@ -584,6 +241,8 @@ static EncodeTiledFn encode_tiled()
 
 static int g_num_sms = 0;
 
+int launch_head_tc2(const TcMaps &maps, TcParams &P, int num_sms, cudaStream_t stream); // yc_head_sm100_2cta.cu
+
 int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, unsigned *left_mask,
                         const FusedDetect *fused, cudaStream_t stream)
 {
@@ -610,6 +269,12 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     // (K=128 x 2 stages measured 6 us slower on the C2 batch; YC_TC_BK overrides for experiments.)
     int bk = 64;
     { const char *e = getenv("YC_TC_BK"); if (e && (atoi(e) == 64 || atoi(e) == 128)) bk = atoi(e); }
+    // CTA pairs (cta_group::2) for the fused step: see yc_head_sm100_2cta.cu.  Experimental (measured 98 us against
+    // 86 us for the 1-CTA kernel on the C2 batch), so opt-in with YC_TC_2CTA=1.
+    bool pair = false;
+    { const char *e = getenv("YC_TC_2CTA"); if (e && atoi(e) == 1) pair = fused != nullptr && n_groups == 1 && npad % 16 == 0; }
+    if (pair) bk = 128; // must equal T2_BK of yc_head_sm100_2cta.cu (feature-map box height)
+    const int tile_px = pair ? 2 * TC_BM : TC_BM;
     const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * TC_B_BOX_BYTES;
     const size_t fixed = 1024 + (size_t)4 * na_tile * slab_bytes + 256;
     int stages = TC_MAX_STAGES;
@@ -651,8 +316,8 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         P.bins = d->bins;
     }
     P.z = d->z;
-    P.idesc = instr_desc_f16(/*bf16*/ 1, /*A MN-major*/ 1, /*B K-major*/ 0, TC_BM, (uint32_t)npad);
-    P.b_box_bytes = (uint32_t)npad * 64 * 2;
+    P.idesc = instr_desc_f16(/*bf16*/ 1, /*A MN-major*/ 1, /*B K-major*/ 0, (uint32_t)tile_px, (uint32_t)npad);
+    P.b_box_bytes = (uint32_t)(pair ? npad / 2 : npad) * 64 * 2;
     P.slab_bytes = slab_bytes;
     P.stages = stages;
     { const char *e = getenv("YC_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
@@ -671,7 +336,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         L.sb = bv.sb;
         L.raw = lv.raw;
         L.K = lv.K; L.HW = HW; L.nx = lv.W;
-        L.tiles_per_img = (HW + TC_BM - 1) / TC_BM;
+        L.tiles_per_img = (HW + tile_px - 1) / tile_px;
         L.n_groups = n_groups;
         L.bmap0 = s * n_groups;
         L.tile_begin = tiles;
@@ -692,7 +357,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
             const int row0 = g * na_tile * d->no;  // rows past Npad_total are zero-filled by TMA
             cuuint64_t gdim[2] = {(cuuint64_t)lv.K, (cuuint64_t)(npad_total - row0)};
             cuuint64_t gstr[1] = {(cuuint64_t)lv.K * 2};
-            cuuint32_t box[2] = {64, (cuuint32_t)npad}, est[2] = {1, 1};
+            cuuint32_t box[2] = {64, (cuuint32_t)(pair ? npad / 2 : npad)}, est[2] = {1, 1};
             CUresult r = enc(&maps.b[s * n_groups + g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                              (void *)(bv.w_bf + (size_t)row0 * lv.K), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -707,6 +372,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         YC_CUDA(cudaGetDevice(&dev));
         YC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    if (pair) return launch_head_tc2(maps, P, g_num_sms, stream);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     const int threads = TC_NON_EPI_THREADS + 128 * na_tile;
     if (bk == 128) {

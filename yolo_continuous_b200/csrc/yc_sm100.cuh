@@ -121,6 +121,76 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar)
                  : "memory");
 }
 
+
+// ---- cluster / cta_group::2 (CTA pair) ------------------------------------------------------------
+// Shared-memory addresses of a CTA carry its cluster rank in bit 24; clearing it addresses the same
+// offset in the pair's leader CTA (rank 0).
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in the leader CTA (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_addr(bar) & PEER_BIT_MASK) : "memory");
+}
+// TMA loads issued by either CTA of a pair; the bytes are accounted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_addr(dst)),
+        "l"(m), "r"(smem_addr(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+        "[%2];" ::"r"(smem_addr(dst)),
+        "l"(m), "r"(smem_addr(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (128 rows from each CTA) * B (N/2 rows from each CTA); issued by the leader only
+__device__ __forceinline__ void mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior MMAs of this thread arrives on `bar` in BOTH CTAs of the pair
+__device__ __forceinline__ void mma_commit_pair(uint64_t *bar)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_addr(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x W consecutive 32-bit columns
 template <int W> struct TmemLd;
 template <> struct TmemLd<1> {
