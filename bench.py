@@ -29,7 +29,7 @@ CH = (256, 512, 1024)
 SHAPES = [(80, 80), (40, 40), (20, 20)]
 STRIDES = [8.0, 16.0, 32.0]
 NC = 80
-CONF, IOU = 0.25, 0.45
+CONF, IOU = float(os.environ.get("YC_BENCH_CONF", "0.25")), 0.45   # YC_BENCH_CONF: kernel experiments only
 INPUT_SHAPE, IMAGE_SHAPE = (640, 640), (512, 773)
 BYTES_PER_IMG = {"bf16": 2867200 * 2 + 25200 * 85 * 4, "fp32": 2867200 * 4 + 25200 * 85 * 4}  # S1: maps in + z out
 BYTES_PER_IMG_FUSED = {"bf16": 2867200 * 2, "fp32": 2867200 * 4}                              # S3: maps in (+28 B/candidate)

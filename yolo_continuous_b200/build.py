@@ -13,6 +13,9 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
 
+EXTRA = os.environ.get("YC_NVCC_FLAGS", "").split()   # experiments only (e.g. -DT2_BK=64)
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
@@ -32,7 +35,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = src[:-3] + ".o"
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [NVCC] + FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     ok = True

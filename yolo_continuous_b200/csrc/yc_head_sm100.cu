@@ -21,7 +21,9 @@
 
 namespace yc {
 
-template <int BK>
+// DBG instantiations honour the YC_TC_DEBUG timing switches (bit 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA,
+// 8 print clock64 wait statistics of CTA 0); the production instantiation carries none of that code.
+template <int BK, bool DBG>
 __global__ void __launch_bounds__(TC_NON_EPI_THREADS + 128 * 3, 1)
 head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
@@ -67,96 +69,115 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    // The producer and the MMA issuer are single threads; each k-block costs them a fixed ~0.3 us of
-    // mbarrier / tcgen05.commit round trips (measured: the bare synchronisation skeleton of this kernel
-    // with K=32 stages took 88 us for the C2 batch), so a stage carries K=64: four MMAs per round trip.
+    // Producer and MMA issuer: the WHOLE warp runs the loop (uniform control flow keeps barrier addresses and
+    // descriptors in uniform registers) and one elected lane issues the TMA / tcgen05 instructions.  Issuing from
+    // inside an `if (lane == 0)` region instead makes ptxas wrap every uniform-datapath instruction in an
+    // ELECT / R2UR / BRA.U.ANY loop and rebuild both descriptors with ~15 dependent uniform ops per MMA: measured
+    // ~165 cycles per issued MMA against the 128-cycle tensor pipe floor (tools/mma_probe.cu: 130 cycles with
+    // descriptors formed by one 64-bit add).
+    const bool skip_epi = DBG && (P.debug & 1), skip_mma = DBG && (P.debug & 2), skip_tma = DBG && (P.debug & 4);
+    const bool prof = DBG && (P.debug & 8) && blockIdx.x == 0;
+    // polling experiments (DBG only): 16 = one epilogue thread polls tfull, the others wait at a named barrier;
+    // 32 / 64 = only lane 0 of the producer / MMA warp polls
+    const bool epi_one = DBG && (P.debug & 16), prod_one = DBG && (P.debug & 32), mma_one = DBG && (P.debug & 64);
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            // Weight residency: when a level has exactly n_stages k-blocks and a tile starts at ring slot 0,
-            // k-block kb of W always lands in slot kb.  After one such tile the B halves of all slots hold
-            // the whole W of that level, so the following tiles of the same level load only A (the MMA
-            // thread is unaware: it reads B from the slot as usual; a slot's B half is only ever written
-            // by this thread, after the slot's empty barrier).
-            int resident_lv = -1;
-            const bool prof = (P.debug & 8) && blockIdx.x == 0;
-            long long p_wait = 0, p_t0 = clock64();
-            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-                const TileCoord tc = tile_coord(P, t);
-                const int nkb = (P.lv[tc.lv].K + TC_BK - 1) / TC_BK;
-                const bool aligned = nkb == n_stages && stage == 0;
-                const int wkey = tc.lv * YC_MAX_ANCHORS + tc.g; // identifies the weight tile
-                const bool load_b = !(aligned && resident_lv == wkey);
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const long long w0 = prof ? clock64() : 0;
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    if (prof) p_wait += clock64() - w0;
+        int stage = 0;
+        uint32_t phase = 0;
+        // Weight residency: when a level has exactly n_stages k-blocks and a tile starts at ring slot 0,
+        // k-block kb of W always lands in slot kb.  After one such tile the B halves of all slots hold
+        // the whole W of that level, so the following tiles of the same level load only A (the MMA
+        // thread is unaware: it reads B from the slot as usual; a slot's B half is only ever written
+        // by this warp, after the slot's empty barrier).
+        int resident_lv = -1;
+        long long p_wait = 0, p_issue = 0, p_t0 = DBG ? clock64() : 0;
+        for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+            const TileCoord tc = tile_coord(P, t);
+            const int nkb = (P.lv[tc.lv].K + TC_BK - 1) / TC_BK;
+            const bool aligned = nkb == n_stages && stage == 0;
+            const int wkey = tc.lv * YC_MAX_ANCHORS + tc.g; // identifies the weight tile
+            const bool load_b = !(aligned && resident_lv == wkey);
+            const CUtensorMap *ma = &maps.a[tc.lv], *mb = &maps.b[P.lv[tc.lv].bmap0 + tc.g];
+            const uint32_t tx = (uint32_t)TC_A_BYTES + (load_b ? (BK / 64) * P.b_box_bytes : 0u);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const long long w0 = prof ? clock64() : 0;
+                if (prod_one) { if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1u); __syncwarp(); }
+                else mbar_wait(&empty_bar[stage], phase ^ 1u);
+                const long long w1 = prof ? clock64() : 0;
+                if (prof) p_wait += w1 - w0;
+                if (elect_one()) {
                     uint8_t *sa = stage_base + stage * TC_STAGE_BYTES, *sb = sa + TC_A_BYTES;
-                    if (P.debug & 4) {
+                    if (skip_tma) {
                         mbar_arrive(&full_bar[stage]);
                     } else {
-                        mbar_arrive_expect_tx(&full_bar[stage],
-                                              (uint32_t)TC_A_BYTES + (load_b ? (BK / 64) * P.b_box_bytes : 0u));
-                        tma_load_3d(sa, &maps.a[tc.lv], &full_bar[stage], tc.p0, kb * TC_BK, tc.b);
-                        tma_load_3d(sa + TC_A_BYTES / 2, &maps.a[tc.lv], &full_bar[stage], tc.p0 + 64, kb * TC_BK, tc.b);
+                        mbar_arrive_expect_tx(&full_bar[stage], tx);
+                        tma_load_3d(sa, ma, &full_bar[stage], tc.p0, kb * TC_BK, tc.b);
+                        tma_load_3d(sa + TC_A_BYTES / 2, ma, &full_bar[stage], tc.p0 + 64, kb * TC_BK, tc.b);
                         if (load_b) {
 #pragma unroll
                             for (int j = 0; j < BK / 64; ++j)
-                                tma_load_2d(sb + j * TC_B_BOX_BYTES, &maps.b[P.lv[tc.lv].bmap0 + tc.g], &full_bar[stage],
-                                            kb * TC_BK + j * 64, 0);
+                                tma_load_2d(sb + j * TC_B_BOX_BYTES, mb, &full_bar[stage], kb * TC_BK + j * 64, 0);
                         }
                     }
-                    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                 }
-                resident_lv = aligned ? wkey : -1;
+                __syncwarp();
+                if (prof) p_issue += clock64() - w1;
+                if (++stage == n_stages) { stage = 0; phase ^= 1u; }
             }
-            if (prof) printf("[yc prof] producer: total %lld cyc, waiting on empty %lld\n", clock64() - p_t0, p_wait);
+            resident_lv = aligned ? wkey : -1;
         }
+        if (prof && lane == 0) printf("[yc prof] producer: total %lld cyc, waiting on empty %lld, issuing %lld\n", clock64() - p_t0, p_wait, p_issue);
     } else if (warp == 1) {
-        // ===================== MMA issuer (one elected lane) =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            const bool prof = (P.debug & 8) && blockIdx.x == 0;
-            long long m_wt = 0, m_wf = 0, m_t0 = clock64();
-            int m_kb = 0;
-            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
-                const TileCoord tc = tile_coord(P, t);
-                const int nkb = (P.lv[tc.lv].K + TC_BK - 1) / TC_BK;
-                const int buf = it & 1;
-                long long w0 = prof ? clock64() : 0;
-                mbar_wait(&tempty_bar[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u); // epilogue drained this buffer
-                if (prof) m_wt += clock64() - w0;
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        long long m_wt = 0, m_wf = 0, m_is = 0, m_t0 = DBG ? clock64() : 0;
+        int m_kb = 0;
+        // A: MN-major SW128: 64-px chunks LBO = BK*128 B apart (one {64 px, BK k} box each), 8-k groups SBO = 1024 B
+        //    apart; one k16 step = two 8-k groups = 2048 B
+        // B: K-major SW128, one box per 64 k: 8-row groups SBO = 1024 B apart; k16 step = 32 B inside the 128-B row
+        // The start-address field holds (address >> 4) in the low 14 bits: stage / k offsets are plain adds.
+        const uint32_t s0 = smem_addr(stage_base);
+        const uint64_t da0 = smem_desc(s0, TC_A_BYTES / 2, 1024, SWZ_128B);
+        const uint64_t db0 = smem_desc(s0 + TC_A_BYTES, 16, 1024, SWZ_128B);
+        const uint32_t idesc = P.idesc;
+        for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+            const TileCoord tc = tile_coord(P, t);
+            const int nkb = (P.lv[tc.lv].K + TC_BK - 1) / TC_BK;
+            const int buf = it & 1;
+            long long w0 = prof ? clock64() : 0;
+            mbar_wait(&tempty_bar[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u); // epilogue drained this buffer
+            if (prof) m_wt += clock64() - w0;
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_MAX_N;
+            for (int kb = 0; kb < nkb; ++kb) {
+                w0 = prof ? clock64() : 0;
+                if (mma_one) { if (lane == 0) mbar_wait(&full_bar[stage], phase); __syncwarp(); }
+                else mbar_wait(&full_bar[stage], phase);
+                const long long w1 = prof ? clock64() : 0;
+                if (prof) { m_wf += w1 - w0; ++m_kb; }
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_MAX_N;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    w0 = prof ? clock64() : 0;
-                    mbar_wait(&full_bar[stage], phase);
-                    if (prof) { m_wf += clock64() - w0; ++m_kb; }
-                    tc_fence_after();
-                    const uint32_t sa = smem_addr(stage_base + stage * TC_STAGE_BYTES), sb = sa + TC_A_BYTES;
+                if (elect_one()) {
+                    const uint64_t so = (uint64_t)((uint32_t)(stage * TC_STAGE_BYTES) >> 4);
+                    if (!skip_mma) {
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k) {
-                        // A: MN-major SW128: 64-px chunks LBO = BK*128 B apart (one {64 px, BK k} box each),
-                        //    8-k groups SBO = 1024 B apart; one k16 step = two 8-k groups = 2048 B
-                        const uint64_t da = smem_desc(sa + k * 2048, TC_A_BYTES / 2, 1024, SWZ_128B);
-                        // B: K-major SW128, one box per 64 k: 8-row groups SBO = 1024 B apart; k16 step = 32 B
-                        //    inside the 128-B row
-                        const uint64_t db = smem_desc(sb + (k / 4) * TC_B_BOX_BYTES + (k % 4) * 32, 16, 1024, SWZ_128B);
-                        if (!(P.debug & 2)) mma_f16(tmem_d, da, db, P.idesc, (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < TC_BK / 16; ++k)
+                            mma_f16(tmem_d, da0 + so + (uint64_t)((k * 2048) >> 4),
+                                    db0 + so + (uint64_t)(((k / 4) * TC_B_BOX_BYTES + (k % 4) * 32) >> 4), idesc,
+                                    (uint32_t)((kb | k) != 0));
                     }
                     mma_commit(&empty_bar[stage]); // frees the smem slot when these MMAs retire
                     if (kb == nkb - 1) mma_commit(&tfull_bar[buf]);
-                    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                if (prof) m_is += clock64() - w1;
+                if (++stage == n_stages) { stage = 0; phase ^= 1u; }
             }
-            if (prof)
-                printf("[yc prof] mma: total %lld cyc, %d tiles %d k-blocks, waiting on tmem-empty %lld, on smem-full %lld\n",
-                       clock64() - m_t0, it, m_kb, m_wt, m_wf);
         }
+        if (prof && lane == 0)
+            printf("[yc prof] mma: total %lld cyc, %d tiles %d k-blocks, waiting on tmem-empty %lld, on smem-full %lld, issuing %lld\n",
+                   clock64() - m_t0, it, m_kb, m_wt, m_wf, m_is);
     } else if (warp >= TC_NON_EPI_THREADS / 32) {
         // ===================== epilogue: TMEM -> sigmoid/decode -> slab -> bulk store =====================
         const int e = warp - TC_NON_EPI_THREADS / 32;
@@ -164,7 +185,8 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int a = e >> 2;       // anchor handled by this warp
         float *slab = (float *)((uint8_t *)slabs + (size_t)e * P.slab_bytes);
         const int no = P.no, no_out = P.no_out;
-        int it = 0;
+        int it = 0, cur_lv = -1;
+        BoxSb sbv;
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
             const TileCoord tc = tile_coord(P, t);
             const TcLevel &L = P.lv[tc.lv];
@@ -178,16 +200,25 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const float2 *sb = L.sb + ar * no;
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_MAX_N + a * no);
 
-            mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
+            if (P.fused && tc.lv != cur_lv) { // fused mode: one anchor group per tile, so `ar` is fixed for this warp
+                sbv = load_box_sb(sb, lane, P.nc);
+                cur_lv = tc.lv;
+            }
+            if (epi_one) {
+                if (e == 0) { if (lane == 0) mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u); __syncwarp(); }
+                named_bar_sync(1, 32 * n_epi_warps);
+            } else {
+                mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
+            }
             tc_fence_after();
-            if (P.debug & 1) {
+            if (skip_epi) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[buf]);
                 continue;
             }
             if (P.fused) {
-                fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane);
+                fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane, sbv);
                 continue;
             }
             if (L.raw) {
@@ -273,7 +304,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     // 86 us for the 1-CTA kernel on the C2 batch), so opt-in with YC_TC_2CTA=1.
     bool pair = false;
     { const char *e = getenv("YC_TC_2CTA"); if (e && atoi(e) == 1) pair = fused != nullptr && n_groups == 1 && npad % 16 == 0; }
-    if (pair) bk = 128; // must equal T2_BK of yc_head_sm100_2cta.cu (feature-map box height)
+    if (pair) bk = T2_BK; // feature-map box height of the CTA-pair kernel
     const int tile_px = pair ? 2 * TC_BM : TC_BM;
     const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * TC_B_BOX_BYTES;
     const size_t fixed = 1024 + (size_t)4 * na_tile * slab_bytes + 256;
@@ -375,13 +406,10 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     if (pair) return launch_head_tc2(maps, P, g_num_sms, stream);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     const int threads = TC_NON_EPI_THREADS + 128 * na_tile;
-    if (bk == 128) {
-        YC_CUDA(cudaFuncSetAttribute(head_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        head_tc_kernel<128><<<grid, threads, smem_bytes, stream>>>(maps, P);
-    } else {
-        YC_CUDA(cudaFuncSetAttribute(head_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        head_tc_kernel<64><<<grid, threads, smem_bytes, stream>>>(maps, P);
-    }
+    void (*kern)(const TcMaps, const TcParams) = P.debug ? (bk == 128 ? head_tc_kernel<128, true> : head_tc_kernel<64, true>)
+                                                         : (bk == 128 ? head_tc_kernel<128, false> : head_tc_kernel<64, false>);
+    YC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kern<<<grid, threads, smem_bytes, stream>>>(maps, P);
     YC_CUDA(cudaGetLastError());
     return YC_OK;
 }

@@ -8,8 +8,9 @@
 // Half a weight k-block being 16 KB, eight weight slots hold all of W for K <= 512 (P3 and P4 of the COCO
 // head), so those levels stream only feature maps; the feature-map ring is separate and as deep as fits.
 //
-// Roles per CTA: warp 0 TMA producer (own A tile + own half of B, bytes accounted on the LEADER's barriers),
-// warp 1 MMA issuer (leader only), warp 2 TMEM allocator, 12 epilogue warps (fused epilogue of yc_head_tc.cuh).
+// Roles per CTA: warp 0 feature-map producer (own A tile), warp 2 TMEM allocator then weight producer (own half of
+// the weight rows), bytes accounted on the LEADER's barriers; warps 1 and 3 MMA issuers (leader only, alternating
+// tiles / TMEM buffers); 12 epilogue warps (fused epilogue of yc_head_tc.cuh).
 // Barriers: a_full/b_full live in the leader (both producers' TMA complete there); a_empty/b_empty/tfull are
 // signalled in both CTAs by multicast tcgen05.commit; tempty lives in the leader and counts the epilogue warps
 // of both CTAs.
@@ -17,14 +18,11 @@
 
 namespace yc {
 
-#ifndef T2_BK
-#define T2_BK 128                              // k per stage: the multicast commits cost ~250 cycles per stage
-#endif
 constexpr int T2_A_BYTES = TC_BM * T2_BK * 2;  // this CTA's 128 pixels x BK k (two {64 px, BK k} boxes)
 constexpr int T2_B_BOX = 128 * 64 * 2;         // 16 KB: this CTA's (up to) 128 weight rows x 64 k
 constexpr int T2_B_BYTES = (T2_BK / 64) * T2_B_BOX;
 #ifndef T2_B_SLOTS_K
-#define T2_B_SLOTS_K 256                       // weight slots cover K <= this (resident weights)
+#define T2_B_SLOTS_K 512                       // weight slots cover K <= this (resident weights): 128 KB per CTA
 #endif
 constexpr int T2_B_SLOTS = T2_B_SLOTS_K / T2_BK;
 constexpr int T2_MAX_A_STAGES = 8;
@@ -36,6 +34,14 @@ struct T2Ring { // carved identically in both CTAs
     uint32_t *tmem_ptr;
 };
 
+// advance a ring position by n stages
+__device__ __forceinline__ void ring_advance(int &s, uint32_t &parity, int n, int depth)
+{
+    s += n;
+    while (s >= depth) { s -= depth; parity ^= 1u; }
+}
+
+template <bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_NON_EPI_THREADS + 128 * 3, 1)
 head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
@@ -76,9 +82,10 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
             mbar_init(&R.b_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&R.tfull[i], 1);
+            mbar_init(&R.tfull[i], 2);   // one commit from each MMA warp
             mbar_init(&R.tempty[i], (uint32_t)(2 * n_epi_warps)); // epilogue warps of both CTAs
         }
+        *(volatile int *)(R.tmem_ptr + 1) = 0;   // `turn` counter of the two MMA warps
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_pair(R.tmem_ptr, TC_TMEM_COLS);
@@ -88,117 +95,140 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
     tc_fence_after();
     const uint32_t tmem_base = *R.tmem_ptr;
 
-    // Weight slot of k-block kb is kb % 8 in every tile; a slot's parity bit flips on every reload, so the
-    // slots need no common ring position.  A level with <= 8 k-blocks keeps its whole W (this CTA's half) in
-    // the slots: consecutive tiles with the same weight tile skip the weight loads altogether.  Producer (both
-    // CTAs) and MMA issuer derive `load_b` from the same deterministic tile sequence.
+    // Every role walks the same deterministic tile sequence t = pair, pair + n_pairs, ... and derives from it the
+    // ring positions and `load_b` (whether the weight tile has to be (re)loaded: a level whose k-blocks all fit the
+    // weight slots keeps its W resident, so only the first of consecutive tiles with the same weight tile loads it).
+    // All role loops are whole-warp loops with one elected issuing lane (see yc_head_sm100.cu for why).
+    const bool skip_epi = DBG && (P.debug & 1), skip_mma = DBG && (P.debug & 2), skip_tma = DBG && (P.debug & 4);
+    const bool spin_epi = DBG && (P.debug & 16), spin_mma = DBG && (P.debug & 32);   // polling experiments
     if (warp == 0) {
-        // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
-            int sa = 0, it = 0, resident = -1;
-            uint32_t pa = 0, pbits = 0; // pbits: bit s = parity of the next load into weight slot s
-            const bool prof = (P.debug & 8) && blockIdx.x < 2;
-            long long w_a = 0, w_b = 0, t0 = clock64();
-            for (int t = pair; t < P.total_tiles; t += n_pairs, ++it) {
-                const TileCoord tc = tile_coord_w(P, t, 2 * TC_BM);
-                const TcLevel &L = P.lv[tc.lv];
-                const int nkb = (L.K + T2_BK - 1) / T2_BK;
-                const int wkey = tc.lv * YC_MAX_ANCHORS + tc.g;
-                const bool load_b = !(nkb <= T2_B_SLOTS && resident == wkey);
-                const int p_own = tc.p0 + TC_BM * (int)rank;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    if (load_b) {
-                        const int s = kb % T2_B_SLOTS;
-                        long long c0 = prof ? clock64() : 0;
-                        mbar_wait(&R.b_empty[s], ((pbits >> s) & 1u) ^ 1u);
-                        if (prof) w_b += clock64() - c0;
-                        if (P.debug & 4) {
-                            if (rank == 0) mbar_arrive(&R.b_full[s]);
-                        } else {
-                            if (rank == 0) mbar_arrive_expect_tx(&R.b_full[s], 2u * (T2_BK / 64) * P.b_box_bytes);
-#pragma unroll
-                            for (int j = 0; j < T2_BK / 64; ++j)
-                                tma_load_2d_pair(R.b_slots + s * T2_B_BYTES + j * T2_B_BOX, &maps.b[L.bmap0 + tc.g], &R.b_full[s],
-                                                 kb * T2_BK + j * 64, (int)rank * (P.npad / 2));
-                        }
-                        pbits ^= 1u << s;
-                    }
-                    long long c1 = prof ? clock64() : 0;
-                    mbar_wait(&R.a_empty[sa], pa ^ 1u);
-                    if (prof) w_a += clock64() - c1;
+        // ===================== feature-map (A) producer, both CTAs =====================
+        int sa = 0;
+        uint32_t pa = 0;
+        for (int t = pair; t < P.total_tiles; t += n_pairs) {
+            const TileCoord tc = tile_coord_w(P, t, 2 * TC_BM);
+            const int nkb = (P.lv[tc.lv].K + T2_BK - 1) / T2_BK;
+            const int p_own = tc.p0 + TC_BM * (int)rank;
+            const CUtensorMap *ma = &maps.a[tc.lv];
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&R.a_empty[sa], pa ^ 1u);
+                if (elect_one()) {
                     uint8_t *dst = R.a_ring + sa * T2_A_BYTES;
-                    if (P.debug & 4) {
+                    if (skip_tma) {
                         if (rank == 0) mbar_arrive(&R.a_full[sa]);
                     } else {
                         if (rank == 0) mbar_arrive_expect_tx(&R.a_full[sa], 2u * (uint32_t)T2_A_BYTES);
-                        tma_load_3d_pair(dst, &maps.a[tc.lv], &R.a_full[sa], p_own, kb * T2_BK, tc.b);
-                        tma_load_3d_pair(dst + T2_A_BYTES / 2, &maps.a[tc.lv], &R.a_full[sa], p_own + 64, kb * T2_BK, tc.b);
+                        tma_load_3d_pair(dst, ma, &R.a_full[sa], p_own, kb * T2_BK, tc.b);
+                        tma_load_3d_pair(dst + T2_A_BYTES / 2, ma, &R.a_full[sa], p_own + 64, kb * T2_BK, tc.b);
                     }
-                    if (++sa == na_st) { sa = 0; pa ^= 1u; }
                 }
-                resident = nkb <= T2_B_SLOTS ? wkey : -1;
+                __syncwarp();
+                if (++sa == na_st) { sa = 0; pa ^= 1u; }
             }
-            if (prof)
-                printf("[yc prof2] producer rank %u: total %lld cyc, waiting a_empty %lld, b_empty %lld\n", rank,
-                       clock64() - t0, w_a, w_b);
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA, one lane) =====================
-        if (lane == 0 && rank == 0) {
-            int sa = 0, it = 0, resident = -1;
+    } else if (warp == 2) {
+        // ===================== weight (B) producer, both CTAs: own half of the weight rows =====================
+        int resident = -1;
+        uint32_t pbits = 0; // bit s = parity of the next load into weight slot s
+        for (int t = pair; t < P.total_tiles; t += n_pairs) {
+            const TileCoord tc = tile_coord_w(P, t, 2 * TC_BM);
+            const TcLevel &L = P.lv[tc.lv];
+            const int nkb = (L.K + T2_BK - 1) / T2_BK;
+            const int wkey = tc.lv * YC_MAX_ANCHORS + tc.g;
+            const bool load_b = !(nkb <= T2_B_SLOTS && resident == wkey);
+            resident = nkb <= T2_B_SLOTS ? wkey : -1;
+            if (!load_b) continue;
+            const CUtensorMap *mb = &maps.b[L.bmap0 + tc.g];
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % T2_B_SLOTS;
+                mbar_wait(&R.b_empty[s], ((pbits >> s) & 1u) ^ 1u);
+                pbits ^= 1u << s;
+                if (elect_one()) {
+                    if (skip_tma) {
+                        if (rank == 0) mbar_arrive(&R.b_full[s]);
+                    } else {
+                        if (rank == 0) mbar_arrive_expect_tx(&R.b_full[s], 2u * (T2_BK / 64) * P.b_box_bytes);
+#pragma unroll
+                        for (int j = 0; j < T2_BK / 64; ++j)
+                            tma_load_2d_pair(R.b_slots + s * T2_B_BYTES + j * T2_B_BOX, mb, &R.b_full[s], kb * T2_BK + j * 64,
+                                             (int)rank * (P.npad / 2));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // ===================== MMA issuers (leader CTA): warp 1 issues the even k-blocks of every tile, warp 3 the
+        // odd ones.  One stage hand-over (barrier poll, fence, election, commits) costs an issuing warp ~300 cycles
+        // in which the tensor pipe, whose queue is only ~2 instructions deep, runs dry (measured: MMA-only time =
+        // 128 cycles x MMAs + 300 cycles x stages); with two warps the hand-over of one hides behind the MMAs of the
+        // other.  Both accumulate into the same TMEM tile and the k-blocks must be added in a fixed order (fp32
+        // accumulation is order dependent: results stay bit-identical to the 1-CTA kernel and run to run), so the
+        // warps pass a `turn` counter (k-blocks issued so far) through shared memory: everything but the MMA issue
+        // itself is done before a warp's turn comes.  Each warp commits its own MMAs (tfull counts 2).
+        if (rank == 0) {
+            const int me = warp == 3 ? 1 : 0;
+            int sa = 0, it = 0, resident = -1, g = 0;   // g: global k-block counter of the pair
             uint32_t pa = 0, pbits = 0;
-            const bool prof = (P.debug & 8) && blockIdx.x == 0;
-            long long w_t = 0, w_a = 0, w_b = 0, t0 = clock64();
-            int n_kb = 0;
+            const uint64_t da0 = smem_desc(smem_addr(R.a_ring), T2_A_BYTES / 2, 1024, SWZ_128B);
+            const uint64_t db0 = smem_desc(smem_addr(R.b_slots), 16, 1024, SWZ_128B);
+            const uint32_t idesc = P.idesc;
+            volatile int *turn = (volatile int *)(R.tmem_ptr + 1);
             for (int t = pair; t < P.total_tiles; t += n_pairs, ++it) {
                 const TileCoord tc = tile_coord_w(P, t, 2 * TC_BM);
-                const TcLevel &L = P.lv[tc.lv];
-                const int nkb = (L.K + T2_BK - 1) / T2_BK;
+                const int nkb = (P.lv[tc.lv].K + T2_BK - 1) / T2_BK;
                 const int wkey = tc.lv * YC_MAX_ANCHORS + tc.g;
                 const bool load_b = !(nkb <= T2_B_SLOTS && resident == wkey);
-                const int buf = it & 1;
-                long long c0 = prof ? clock64() : 0;
-                mbar_wait(&R.tempty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u); // both CTAs' epilogues drained the buffer
-                if (prof) w_t += clock64() - c0;
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_MAX_N;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const int s = kb % T2_B_SLOTS;
-                    if (load_b) {
-                        c0 = prof ? clock64() : 0;
-                        mbar_wait(&R.b_full[s], (pbits >> s) & 1u);
-                        if (prof) w_b += clock64() - c0;
-                        pbits ^= 1u << s;
-                    }
-                    c0 = prof ? clock64() : 0;
-                    mbar_wait(&R.a_full[sa], pa);
-                    if (prof) { w_a += clock64() - c0; ++n_kb; }
-                    tc_fence_after();
-                    const uint32_t aaddr = smem_addr(R.a_ring + sa * T2_A_BYTES);
-                    const uint32_t baddr = smem_addr(R.b_slots + s * T2_B_BYTES);
-#pragma unroll
-                    for (int k = 0; k < T2_BK / 16; ++k) {
-                        const uint64_t da = smem_desc(aaddr + k * 2048, T2_A_BYTES / 2, 1024, SWZ_128B);
-                        const uint64_t db = smem_desc(baddr + (k / 4) * T2_B_BOX + (k % 4) * 32, 16, 1024, SWZ_128B);
-                        if (!(P.debug & 2)) mma_f16_pair(tmem_d, da, db, P.idesc, (uint32_t)((kb | k) != 0));
-                    }
-                    mma_commit_pair(&R.a_empty[sa]);
-                    if (++sa == na_st) { sa = 0; pa ^= 1u; }
-                    if (load_b) mma_commit_pair(&R.b_empty[s]);
-                    if (kb == nkb - 1) mma_commit_pair(&R.tfull[buf]);
-                }
                 resident = nkb <= T2_B_SLOTS ? wkey : -1;
+                const int buf = it & 1;
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_MAX_N;
+                // both CTAs' epilogues drained the buffer (also orders this warp's tfull arrival after the previous
+                // phase of tfull[buf], which the epilogues waited for)
+                if (spin_mma) mbar_spin(&R.tempty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                else mbar_wait(&R.tempty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = kb % T2_B_SLOTS;
+                    if ((g & 1) == me) {
+                        if (load_b) mbar_wait(&R.b_full[s], (pbits >> s) & 1u);
+                        if (spin_mma) mbar_spin(&R.a_full[sa], pa);
+                        else mbar_wait(&R.a_full[sa], pa);
+                        tc_fence_after();
+                        const uint64_t da = da0 + (uint64_t)((uint32_t)(sa * T2_A_BYTES) >> 4);
+                        const uint64_t db = db0 + (uint64_t)((uint32_t)(s * T2_B_BYTES) >> 4);
+                        while (*turn != g) { }
+                        if (elect_one()) {
+                            if (!skip_mma) {
+#pragma unroll
+                                for (int k = 0; k < T2_BK / 16; ++k)
+                                    mma_f16_pair(tmem_d, da + (uint64_t)((k * 2048) >> 4),
+                                                 db + (uint64_t)(((k / 4) * T2_B_BOX + (k % 4) * 32) >> 4), idesc,
+                                                 (uint32_t)((kb | k) != 0));
+                            }
+                            *turn = g + 1;
+                            mma_commit_pair(&R.a_empty[sa]);
+                            if (load_b) mma_commit_pair(&R.b_empty[s]);
+                        }
+                        __syncwarp();
+                    }
+                    if (load_b) pbits ^= 1u << s;
+                    if (++sa == na_st) { sa = 0; pa ^= 1u; }
+                }
+                // every MMA of the tile precedes the later of the two commits (a warp without a k-block in this
+                // tile still counts)
+                if (elect_one()) mma_commit_pair(&R.tfull[buf]);
+                __syncwarp();
             }
-            if (prof)
-                printf("[yc prof2] mma: total %lld cyc, %d tiles %d k-blocks, waiting tmem-empty %lld, a_full %lld, b_full %lld\n",
-                       clock64() - t0, it, n_kb, w_t, w_a, w_b);
         }
     } else if (warp >= TC_NON_EPI_THREADS / 32) {
         // ===================== fused epilogue (both CTAs) =====================
         const int e = warp - TC_NON_EPI_THREADS / 32;
         const int q = warp & 3, a = e >> 2;
         float *slab = (float *)((uint8_t *)R.queues + (size_t)e * P.slab_bytes);
-        int it = 0;
+        int it = 0, cur_lv = -1;
+        BoxSb sbv;
+        const bool eprof = DBG && (P.debug & 8) && blockIdx.x == 0;
+        long long e_wait = 0, e_work = 0, e_max = 0;
+        int e_slow = 0;
         for (int t = pair; t < P.total_tiles; t += n_pairs, ++it) {
             const TileCoord tc = tile_coord_w(P, t, 2 * TC_BM);
             const TcLevel &L = P.lv[tc.lv];
@@ -207,16 +237,33 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
             const int nv = min(32, L.HW - prow0);
             const int ar = tc.g * P.na + a;
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_MAX_N + a * P.no);
-            mbar_wait(&R.tfull[buf], (uint32_t)(it >> 1) & 1u);
+            if (tc.lv != cur_lv) { // fused mode: one anchor group per tile, so `ar` is fixed for this warp
+                sbv = load_box_sb(L.sb + ar * P.no, lane, P.nc);
+                cur_lv = tc.lv;
+            }
+            const long long e0 = eprof ? clock64() : 0;
+            if (spin_epi) mbar_spin(&R.tfull[buf], (uint32_t)(it >> 1) & 1u);
+            else mbar_wait(&R.tfull[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            if (P.debug & 1) {
+            const long long e1 = eprof ? clock64() : 0;
+            if (skip_epi) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&R.tempty[buf]);
                 continue;
             }
-            fused_epilogue<true>(P, L, tc.b, prow0, nv, ar, taddr, slab, &R.tempty[buf], lane);
+            fused_epilogue<true>(P, L, tc.b, prow0, nv, ar, taddr, slab, &R.tempty[buf], lane, sbv);
+            if (eprof) {
+                const long long e2 = clock64();
+                e_wait += e1 - e0;
+                e_work += e2 - e1;
+                if (e2 - e1 > e_max) e_max = e2 - e1;
+                if (e2 - e1 > 600) ++e_slow;
+            }
         }
+        if (eprof && lane == 0)
+            printf("[yc prof2] epilogue warp %d: %d tiles, waiting tfull %lld, working %lld (max %lld per tile, %d tiles > 600)\n",
+                   e, it, e_wait, e_work, e_max, e_slow);
     }
 
     tc_fence_before();
@@ -235,10 +282,11 @@ int launch_head_tc2(const TcMaps &maps, TcParams &P, int num_sms, cudaStream_t s
     const size_t smem_bytes = fixed + (size_t)stages * T2_A_BYTES;
     YC_REQUIRE(smem_bytes <= 227 * 1024, YC_ERR_UNSUPPORTED, "2-CTA head: needs %zu bytes of shared memory", smem_bytes);
     P.stages = stages;
-    YC_CUDA(cudaFuncSetAttribute(head_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    void (*kern)(const TcMaps, const TcParams) = P.debug ? head_tc2_kernel<true> : head_tc2_kernel<false>;
+    YC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int pairs = num_sms / 2;
     if (P.total_tiles < pairs) pairs = P.total_tiles;
-    head_tc2_kernel<<<2 * pairs, TC_NON_EPI_THREADS + 128 * P.na, smem_bytes, stream>>>(maps, P);
+    kern<<<2 * pairs, TC_NON_EPI_THREADS + 128 * P.na, smem_bytes, stream>>>(maps, P);
     YC_CUDA(cudaGetLastError());
     return YC_OK;
 }

@@ -24,6 +24,9 @@ constexpr int TC_MAX_N = 256;
 //   A stage = two {64 px, BK k} bf16 boxes (BK*128 B each); B stage = BK/64 boxes {64 k, Npad} (32 KB each)
 constexpr int TC_B_BOX_BYTES = TC_MAX_N * 64 * 2;    // 32 KB
 constexpr int TC_TMEM_COLS = 512;
+#ifndef T2_BK
+#define T2_BK 64                 // k per feature-map stage of the CTA-pair kernel (yc_head_sm100_2cta.cu)
+#endif
 constexpr int TC_NON_EPI_THREADS = 128;
 
 struct TcLevel {
@@ -251,6 +254,29 @@ __device__ __forceinline__ void queue_classes(uint32_t taddr, int no, bool pass,
     if (rem & 1) { queue_chunk<1>(taddr, c, pass, qrow); }
 }
 
+// nc = 16 * NCH classes: all class accumulators of this thread's row into registers with ONE wait, so that the TMEM
+// buffer can be handed back before anything is written to the queue
+template <int NCH>
+__device__ __forceinline__ void grab_classes(uint32_t taddr, bool pass, float *__restrict__ qrow, uint64_t *tempty, int lane,
+                                             bool pair)
+{
+    uint32_t v[NCH * 16];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) TmemLd<16>::ld(taddr + 5u + 16u * i, v + 16 * i);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        if (pair) mbar_arrive_leader(tempty);
+        else mbar_arrive(tempty);
+    }
+    if (pass) {
+#pragma unroll
+        for (int j = 0; j < NCH * 16; ++j) qrow[j] = __uint_as_float(v[j]);
+    }
+    __syncwarp();
+}
+
 constexpr int TC_QUEUE_ROWS = 4; // survivors per warp and tile handled through the queue; more -> in-register scan
 
 // warp-cooperative write of `nv` finished rows from the slab to global memory
@@ -274,13 +300,28 @@ __device__ __forceinline__ void slab_store(float *__restrict__ gdst, const float
 // Fused epilogue of one warp for one tile (see yc_detect_fused): reads this warp's 32 rows of the accumulator
 // (anchor `ar`), rejects on objectness, scans the classes of the survivors, emits NMS candidates and hands the
 // TMEM buffer back through `tempty` (PAIR: the barrier lives in the pair's leader CTA).
+// The (scale, bias) pairs of the 4 box columns and the objectness column are loaded by the caller BEFORE it waits
+// for the accumulator (`sbv`), so that nothing but the TMEM load sits between "tile finished" and the early reject.
+// `cls` holds the pairs of the classes lane, lane + 32, lane + 64 (the classes this lane scans for a queued survivor).
+// With 227 KB of shared memory carved out there is next to no L1 left, so every __ldg here is an L2 round trip: the
+// caller keeps the struct in registers and reloads it only when the level changes.
+struct BoxSb { float2 v[5]; float2 cls[3]; };
+__device__ __forceinline__ BoxSb load_box_sb(const float2 *__restrict__ sb, int lane, int nc)
+{
+    BoxSb r;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) r.v[j] = YC_SB(sb + j);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.cls[k] = lane + 32 * k < nc ? YC_SB(sb + 5 + lane + 32 * k) : make_float2(0.f, 0.f);
+    return r;
+}
+
 template <bool PAIR>
 __device__ __forceinline__ void fused_epilogue(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar,
-                                               uint32_t taddr, float *slab, uint64_t *tempty, int lane)
+                                               uint32_t taddr, float *slab, uint64_t *tempty, int lane, const BoxSb &sbv)
 {
     const int no = P.no;
     const int p = prow0 + lane;
-    const float gx = (float)(p % L.nx), gy = (float)(p / L.nx);
     const float aw = L.anchor_wh[2 * ar], ah = L.anchor_wh[2 * ar + 1];
     const float2 *sb = L.sb + ar * no;
     // box + objectness logits (columns 0..4), then the largest class logit
@@ -290,14 +331,8 @@ __device__ __forceinline__ void fused_epilogue(const TcParams &P, const TcLevel 
     tmem_ld_wait();
     float tb[5];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 s_b = YC_SB(sb + j);
-        tb[j] = fmaf(__uint_as_float(v4[j]), s_b.x, s_b.y);
-    }
-    {
-        const float2 s_b = YC_SB(sb + 4);
-        tb[4] = fmaf(__uint_as_float(v1[0]), s_b.x, s_b.y);
-    }
+    for (int j = 0; j < 4; ++j) tb[j] = fmaf(__uint_as_float(v4[j]), sbv.v[j].x, sbv.v[j].y);
+    tb[4] = fmaf(__uint_as_float(v1[0]), sbv.v[4].x, sbv.v[4].y);
     // Early reject on objectness alone: class scores are sigmoids (<= 1), so obj >= conf is necessary
     // for obj*cls >= conf.  At detection thresholds >99% of rows stop here after 5 columns; only
     // warps holding a survivor scan the class columns (exactly as the z path would see them).
@@ -306,27 +341,53 @@ __device__ __forceinline__ void fused_epilogue(const TcParams &P, const TcLevel 
     const unsigned surv = __ballot_sync(0xffffffffu, pass);
     const int n_surv = __popc(surv);
     if (n_surv > 0 && n_surv <= TC_QUEUE_ROWS) {
-        // Few survivors (the common case): copy their class accumulators to shared memory, hand the
-        // TMEM buffer back at once, then scan the classes with the 32 lanes spread over the classes.
+        // Few survivors (the common case): reserve their candidate slots with ONE atomicAdd (its round trip hides
+        // behind what follows), copy their class accumulators to shared memory, hand the TMEM buffer back at once,
+        // then scan the classes with the 32 lanes spread over the classes.
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&P.ws.cand_count[b], n_surv);
         float *q = slab; // per-warp queue [TC_QUEUE_ROWS][nc]
         const int nc = P.nc;
-        queue_classes(taddr, no, pass, q + __popc(surv & ((1u << lane) - 1u)) * nc);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-            if (PAIR) mbar_arrive_leader(tempty);
-            else mbar_arrive(tempty);
+        float *qrow = q + __popc(surv & ((1u << lane) - 1u)) * nc;
+        switch ((nc & 15) == 0 ? nc >> 4 : 0) {
+        case 1: grab_classes<1>(taddr, pass, qrow, tempty, lane, PAIR); break;
+        case 2: grab_classes<2>(taddr, pass, qrow, tempty, lane, PAIR); break;
+        case 3: grab_classes<3>(taddr, pass, qrow, tempty, lane, PAIR); break;
+        case 4: grab_classes<4>(taddr, pass, qrow, tempty, lane, PAIR); break;
+        case 5: grab_classes<5>(taddr, pass, qrow, tempty, lane, PAIR); break;
+        case 6: grab_classes<6>(taddr, pass, qrow, tempty, lane, PAIR); break;
+        default:
+            queue_classes(taddr, no, pass, qrow);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_leader(tempty);
+                else mbar_arrive(tempty);
+            }
         }
         unsigned left = surv;
+        float my_bv = 0.0f;
+        int my_best = 0, my_src = 0;
         for (int sidx = 0; sidx < n_surv; ++sidx) {
             const int src = __ffs(left) - 1;
             left &= left - 1;
             float bv = -1.0f;
             int best = 0;
-            for (int c = lane; c < nc; c += 32) { // ascending classes per lane: strict > keeps the first
-                const float2 s_b = __ldg(sb + 5 + c);
-                const float sg = sigmoidf_fast(fmaf(q[sidx * nc + c], s_b.x, s_b.y));
-                if (sg > bv) { bv = sg; best = c; }
+            if (nc <= 96) { // ascending classes per lane: strict > keeps the first
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c < nc) {
+                        const float sg = sigmoidf_fast(fmaf(q[sidx * nc + c], sbv.cls[k].x, sbv.cls[k].y));
+                        if (sg > bv) { bv = sg; best = c; }
+                    }
+                }
+            } else {
+                for (int c = lane; c < nc; c += 32) {
+                    const float2 s_b = __ldg(sb + 5 + c);
+                    const float sg = sigmoidf_fast(fmaf(q[sidx * nc + c], s_b.x, s_b.y));
+                    if (sg > bv) { bv = sg; best = c; }
+                }
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) { // larger value wins, ties go to the smaller class
@@ -334,19 +395,26 @@ __device__ __forceinline__ void fused_epilogue(const TcParams &P, const TcLevel 
                 const int oi = __shfl_xor_sync(0xffffffffu, best, off);
                 if (ov > bv || (ov == bv && oi < best)) { bv = ov; best = oi; }
             }
-            const float o_s = __shfl_sync(0xffffffffu, obj, src);
-            const float t0 = __shfl_sync(0xffffffffu, tb[0], src), t1 = __shfl_sync(0xffffffffu, tb[1], src);
-            const float t2 = __shfl_sync(0xffffffffu, tb[2], src), t3 = __shfl_sync(0xffffffffu, tb[3], src);
-            const float score = __fmul_rn(o_s, bv);
-            if (lane == 0 && score >= P.conf) {
-                const int ps = prow0 + src;
+            if (lane == sidx) { my_bv = bv; my_best = best; my_src = src; }
+        }
+        // lane i finishes survivor i: all lanes take part in the shuffles, lanes >= n_surv read lane 0
+        const float o_s = __shfl_sync(0xffffffffu, obj, my_src);
+        const float t0 = __shfl_sync(0xffffffffu, tb[0], my_src), t1 = __shfl_sync(0xffffffffu, tb[1], my_src);
+        const float t2 = __shfl_sync(0xffffffffu, tb[2], my_src), t3 = __shfl_sync(0xffffffffu, tb[3], my_src);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < n_surv) {
+            const float score = __fmul_rn(o_s, my_bv);
+            if (score >= P.conf) {
+                const int ps = prow0 + my_src;
                 const float cx = decode_xy(sigmoidf_fast(t0), (float)(ps % L.nx), L.stride);
                 const float cy = decode_xy(sigmoidf_fast(t1), (float)(ps / L.nx), L.stride);
                 const float bw = decode_wh(sigmoidf_fast(t2), aw), bh = decode_wh(sigmoidf_fast(t3), ah);
                 float x1, y1, x2, y2;
                 xywh_to_corners(cx, cy, bw, bh, P.div_w, P.div_h, x1, y1, x2, y2);
-                emit_one(b, L.row_off + ar * L.HW + ps, P.rows_total, nc, x1, y1, x2, y2, o_s, bv, score, best,
-                         P.ws);
+                emit_at(base + lane, b, L.row_off + ar * L.HW + ps, P.rows_total, nc, x1, y1, x2, y2, o_s, my_bv, score,
+                        my_best, P.ws);
+            } else {
+                emit_hole(base + lane, b, P.rows_total, P.ws);
             }
         }
         __syncwarp();
@@ -359,6 +427,7 @@ __device__ __forceinline__ void fused_epilogue(const TcParams &P, const TcLevel 
         cls_scan<true>(taddr, no, sb, bv, best);
         const float score = __fmul_rn(obj, bv);
         pass = pass && score >= P.conf;
+        const float gx = (float)(p % L.nx), gy = (float)(p / L.nx);
         const float cx = decode_xy(sigmoidf_fast(tb[0]), gx, L.stride);
         const float cy = decode_xy(sigmoidf_fast(tb[1]), gy, L.stride);
         const float bw = decode_wh(sigmoidf_fast(tb[2]), aw), bh = decode_wh(sigmoidf_fast(tb[3]), ah);

@@ -100,6 +100,24 @@ __device__ __forceinline__ void emit_one(int b, int r, int rows, int nc, float x
     atomicAdd(&ws.hist[(size_t)b * nc + cls], 1);
 }
 
+// candidate into a slot reserved beforehand (the fused head epilogue reserves one slot per objectness survivor with a
+// single atomicAdd per warp, issued before the class scan so that its latency is hidden)
+__device__ __forceinline__ void emit_at(int slot, int b, int r, int rows, int nc, float x1, float y1, float x2, float y2,
+                                        float obj, float conf_cls, float score, int cls, const NmsWs &ws)
+{
+    const size_t ib = (size_t)b * rows;
+    ws.box[ib + r] = make_float4(x1, y1, x2, y2);
+    ws.oc[ib + r] = make_float2(obj, conf_cls);
+    ws.key_unsorted[ib + slot] = make_key(score, r);
+    ws.cls_unsorted[ib + slot] = cls;
+    atomicAdd(&ws.hist[(size_t)b * nc + cls], 1);
+}
+// a reserved slot whose row failed the final threshold: skipped by bucket_kernel
+__device__ __forceinline__ void emit_hole(int slot, int b, int rows, const NmsWs &ws)
+{
+    ws.cls_unsorted[(size_t)b * rows + slot] = -1;
+}
+
 // xywh (optionally divided by the input size) -> corners, in the reference's operation order
 // (detect.py:98-103): x1 = cx - w/2 ...
 __device__ __forceinline__ void xywh_to_corners(float cx, float cy, float bw, float bh, float div_w, float div_h, float &x1,

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(256) bucket_kernel(int rows, int nc, NmsWs ws)
     const int s1 = min(n, s0 + BUCKET_SLOTS);
     for (int slot = s0 + tid; slot < s1; slot += 256) {
         const int cls = ws.cls_unsorted[ib + slot];
+        if (cls < 0) continue; // slot reserved by the fused head epilogue for a row that failed obj * cls >= conf
         const int off = cls < BUCKET_SMEM_NC ? s_off[cls] : ws.seg_off[sb + cls];
         const int pos = off + atomicAdd(&ws.cursor[sb + cls], 1);
         ws.key_bucket[ib + pos] = ws.key_unsorted[ib + slot];

@@ -49,10 +49,41 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// non-blocking probe of a phase (never suspends the thread)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {
     }
+}
+
+// named barrier among `nthreads` threads (multiple of 32) of the CTA; id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// busy poll (no hardware suspend between polls)
+__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_test(bar, parity)) {
+    }
+}
+template <bool SPIN> __device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity)
+{
+    if (SPIN) mbar_spin(bar, parity);
+    else mbar_wait(bar, parity);
 }
 
 // ---- TMA -------------------------------------------------------------------------------------
