@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="materialise z (drop-in forward) and run the stand-alone threshold kernel")
+    ap.add_argument("--no-overlap", action="store_true", help="NMS kernels on the head kernel's stream (no second stream)")
     ap.add_argument("--profile", action="store_true", help="device-resident loop only (for ncu runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -180,9 +181,10 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    overlap = not args.no_overlap and not args.unfused and args.dtype == "bf16"
     head = make_head().to(dev)
     pipe = PostBackbone(head, args.bs, SHAPES, tdt, INPUT_SHAPE, IMAGE_SHAPE, True, CONF, IOU, dev, use_graph=False,
-                        fused=not args.unfused, double_buffer=world > 1)
+                        fused=not args.unfused, double_buffer=world > 1, overlap=overlap)
     GATHER_ROWS = 16384   # rows per rank in the fixed-size exchange (C2 produces ~2.7k per 64 images)
     gather = DetectionGather(pipe.message(GATHER_ROWS).numel(), dev) if world > 1 else None
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -190,10 +192,16 @@ def main():
     for d_, h_ in zip(xs, pipe.x_host):
         h_.copy_(d_)
 
+    if overlap:
+        # the head kernel's stream gets the higher priority: its CTAs are placed first, the NMS kernels of the
+        # previous batch (tail stream, default priority) take what is left of each SM
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
+
     def step():
         rows, _, counts, offsets = pipe.run_device(xs)
         if world > 1:
-            gather.gather_async(pipe.message(GATHER_ROWS))   # side stream; overlaps the next step
+            gather.gather_async(pipe.message(GATHER_ROWS), stream=pipe.tail_stream)   # overlaps the next step
         return rows, counts, offsets
 
     def sync_all():
@@ -212,31 +220,12 @@ def main():
     sync_all()
     t0.record()
     for i in range(K):
-        # same launches as pipe.run_device, with the head kernel bracketed by events on its own stream
-        if pipe.n_bufs > 1:
-            pipe.cur ^= 1
-        for j, x in enumerate(xs):
-            pipe.desc.level[j].x = x.data_ptr()
-        s = _lib.stream_ptr(dev)
-        m = pipe.meta.data_ptr()
-        ev[i][0].record()
-        if pipe.fused:
-            _lib.check(_lib.lib.yc_detect_fused_head(pipe.desc, pipe.nms_params, pipe.ws.data_ptr(), pipe.ws.numel(), s),
-                       "yc_detect_fused_head")
-            ev[i][1].record()
-            _lib.check(_lib.lib.yc_nms_from_candidates(pipe.nms_params, pipe.ws.data_ptr(), pipe.ws.numel(),
-                                                       pipe.out_rows.data_ptr(), pipe.out_idx.data_ptr(), m,
-                                                       m + 4 * args.bs, s), "yc_nms_from_candidates")
-        else:
-            _lib.check(_lib.lib.yc_head_forward(pipe.desc, s), "yc_head_forward")
-            ev[i][1].record()
-            _lib.check(_lib.lib.yc_nms_batched(pipe.z.data_ptr(), pipe.nms_params, pipe.ws.data_ptr(), pipe.ws.numel(),
-                                               pipe.out_rows.data_ptr(), pipe.out_idx.data_ptr(), m, m + 4 * args.bs, s),
-                       "yc_nms_batched")
+        pipe.run_device(xs, head_events=ev[i])   # head kernel bracketed by events on its own stream
         if world > 1:
-            gather.gather_async(pipe.message(GATHER_ROWS))
+            gather.gather_async(pipe.message(GATHER_ROWS), stream=pipe.tail_stream)
     if world > 1:
         gather.wait()
+    pipe.wait()
     t1.record()
     sync_all()
     clocks = sampler.stop()
@@ -263,7 +252,7 @@ def main():
     for _ in range(K):
         out = pipe.run_host()
         if world > 1:
-            gather.gather_async(pipe.message(GATHER_ROWS))
+            gather.gather_async(pipe.message(GATHER_ROWS), stream=pipe.tail_stream)
     if world > 1:
         gather.wait()
     torch.cuda.synchronize()

@@ -146,6 +146,13 @@ YC_API int yc_detect_fused_head(const yc_head_desc *desc, const yc_nms_params *p
                          yc_stream_t stream);
 YC_API int yc_nms_from_candidates(const yc_nms_params *p, void *workspace, size_t workspace_bytes, float *out_rows,
                            int32_t *out_idx, int32_t *out_counts, int32_t *out_offsets, yc_stream_t stream);
+/* Pipelined form (NMS kernels of batch i on a second stream next to the head kernel of batch i+1, one workspace per
+ * batch in flight): yc_nms_workspace_reset clears the counters -- enqueue it behind yc_nms_from_candidates on the
+ * NMS stream -- and yc_detect_fused_head_noreset is yc_detect_fused_head for a workspace that is already clear, so
+ * that nothing but the head kernel runs on the head stream. */
+YC_API int yc_nms_workspace_reset(const yc_nms_params *p, void *workspace, size_t workspace_bytes, yc_stream_t stream);
+YC_API int yc_detect_fused_head_noreset(const yc_head_desc *desc, const yc_nms_params *p, void *workspace,
+                                 size_t workspace_bytes, yc_stream_t stream);
 
 /* torchvision.ops.nms drop-in for one box set (detect.py:133): boxes [n,4] xyxy, scores [n].
  * keep [n] receives kept indices in score order, *keep_count_dev their number. workspace from

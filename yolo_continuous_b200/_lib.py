@@ -39,7 +39,7 @@ class NmsParams(C.Structure):
 EXPORTS = ["yc_last_error", "yc_version", "yc_device_check", "yc_head_pack_bytes", "yc_head_pack",
            "yc_head_forward", "yc_decode_box", "yc_nms_workspace_bytes", "yc_nms_batched",
            "yc_nms_single", "yc_box_iou", "yc_cvt_bbox", "yc_detect_fused",
-           "yc_detect_fused_head", "yc_nms_from_candidates"]
+           "yc_detect_fused_head", "yc_nms_from_candidates", "yc_nms_workspace_reset", "yc_detect_fused_head_noreset"]
 
 
 def _load():
@@ -65,6 +65,8 @@ def _load():
     lib.yc_detect_fused.argtypes = [C.POINTER(HeadDesc), C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_detect_fused_head.argtypes = [C.POINTER(HeadDesc), C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.yc_detect_fused_head_noreset.argtypes = lib.yc_detect_fused_head.argtypes
+    lib.yc_nms_workspace_reset.argtypes = [C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.yc_nms_from_candidates.argtypes = [C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_nms_single.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_size_t,

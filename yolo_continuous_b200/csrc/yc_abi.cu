@@ -178,8 +178,20 @@ static int fused_setup(const yc_head_desc *d, const yc_nms_params *p, void *work
     return YC_OK;
 }
 
-extern "C" int yc_detect_fused_head(const yc_head_desc *d, const yc_nms_params *p, void *workspace,
-                                    size_t workspace_bytes, yc_stream_t stream_)
+extern "C" int yc_nms_workspace_reset(const yc_nms_params *p, void *workspace, size_t workspace_bytes, yc_stream_t stream_)
+{
+    YC_REQUIRE(p && workspace, YC_ERR_INVALID, "yc_nms_workspace_reset: null argument");
+    YC_REQUIRE(p->bs > 0 && p->rows > 0 && p->nc > 0, YC_ERR_INVALID, "yc_nms_workspace_reset: bad shape");
+    void *base = (void *)round_up_sz((size_t)workspace, 256);
+    NmsWs ws = carve(base, p->bs, p->rows, p->nc);
+    YC_REQUIRE(ws.total_bytes + ((char *)base - (char *)workspace) <= workspace_bytes, YC_ERR_WORKSPACE,
+               "yc_nms_workspace_reset: workspace %zu < %zu", workspace_bytes, ws.total_bytes + 256);
+    YC_CUDA(cudaMemsetAsync(ws.counters, 0, ws.counters_bytes, (cudaStream_t)stream_));
+    return YC_OK;
+}
+
+static int fused_head(const yc_head_desc *d, const yc_nms_params *p, void *workspace, size_t workspace_bytes, bool reset,
+                      yc_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     int row_off[YC_MAX_LEVELS], rows_total = 0;
@@ -187,12 +199,24 @@ extern "C" int yc_detect_fused_head(const yc_head_desc *d, const yc_nms_params *
     const int src = fused_setup(d, p, workspace, workspace_bytes, row_off, &rows_total, &f);
     if (src != YC_OK) return src;
     // check the shape before touching the workspace, so that an unsupported call has no side effects
-    YC_CUDA(cudaMemsetAsync(f.ws.counters, 0, f.ws.counters_bytes, stream));
+    if (reset) YC_CUDA(cudaMemsetAsync(f.ws.counters, 0, f.ws.counters_bytes, stream));
     unsigned left = 0;
     const int rc = launch_head_tcgen05(d, rows_total, row_off, &left, &f, stream);
     if (rc != YC_OK) return rc;
     YC_REQUIRE(left == 0, YC_ERR_UNSUPPORTED, "yc_detect_fused: levels 0x%x do not fit the tcgen05 kernel: %s", left, g_err);
     return YC_OK;
+}
+
+extern "C" int yc_detect_fused_head(const yc_head_desc *d, const yc_nms_params *p, void *workspace,
+                                    size_t workspace_bytes, yc_stream_t stream)
+{
+    return fused_head(d, p, workspace, workspace_bytes, true, stream);
+}
+
+extern "C" int yc_detect_fused_head_noreset(const yc_head_desc *d, const yc_nms_params *p, void *workspace,
+                                            size_t workspace_bytes, yc_stream_t stream)
+{
+    return fused_head(d, p, workspace, workspace_bytes, false, stream);
 }
 
 extern "C" int yc_nms_from_candidates(const yc_nms_params *p, void *workspace, size_t workspace_bytes, float *out_rows,

@@ -24,7 +24,7 @@ namespace yc {
 // DBG instantiations honour the YC_TC_DEBUG timing switches (bit 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA,
 // 8 print clock64 wait statistics of CTA 0); the production instantiation carries none of that code.
 template <int BK, bool DBG>
-__global__ void __launch_bounds__(TC_NON_EPI_THREADS + 128 * 3, 1)
+__global__ void __maxnreg__(TC_MAX_REGS)
 head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
     constexpr int TC_BK = BK;

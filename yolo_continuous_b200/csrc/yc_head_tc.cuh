@@ -28,6 +28,11 @@ constexpr int TC_TMEM_COLS = 512;
 #define T2_BK 64                 // k per feature-map stage of the CTA-pair kernel (yc_head_sm100_2cta.cu)
 #endif
 constexpr int TC_NON_EPI_THREADS = 128;
+// Register cap of the head kernels: 512 threads x 96 leave a quarter of the SM's register file (and ~19 KB of its
+// shared memory) to the NMS kernels of the previous batch, which run next to the head kernel on a second stream.
+#ifndef TC_MAX_REGS
+#define TC_MAX_REGS 96
+#endif
 
 struct TcLevel {
     const float2 *sb;   // (scale, bias2) per column
@@ -260,10 +265,21 @@ template <int NCH>
 __device__ __forceinline__ void grab_classes(uint32_t taddr, bool pass, float *__restrict__ qrow, uint64_t *tempty, int lane,
                                              bool pair)
 {
-    uint32_t v[NCH * 16];
+    // at most 48 accumulators in registers at a time (the kernel is capped at TC_MAX_REGS registers)
+    constexpr int H1 = NCH > 3 ? 3 : NCH, H2 = NCH - H1;
+    uint32_t v[H1 * 16];
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) TmemLd<16>::ld(taddr + 5u + 16u * i, v + 16 * i);
+    for (int i = 0; i < H1; ++i) TmemLd<16>::ld(taddr + 5u + 16u * i, v + 16 * i);
     tmem_ld_wait();
+    if (H2 > 0) {
+        if (pass) {
+#pragma unroll
+            for (int j = 0; j < H1 * 16; ++j) qrow[j] = __uint_as_float(v[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < H2; ++i) TmemLd<16>::ld(taddr + 5u + 16u * (H1 + i), v + 16 * i);
+        tmem_ld_wait();
+    }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
@@ -272,7 +288,7 @@ __device__ __forceinline__ void grab_classes(uint32_t taddr, bool pass, float *_
     }
     if (pass) {
 #pragma unroll
-        for (int j = 0; j < NCH * 16; ++j) qrow[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < (H2 > 0 ? H2 : H1) * 16; ++j) qrow[(H2 > 0 ? H1 * 16 : 0) + j] = __uint_as_float(v[j]);
     }
     __syncwarp();
 }

@@ -386,7 +386,7 @@ struct CorrectParams {
     int image_hw_stride;
 };
 
-constexpr int FINISH_NT = 512;
+constexpr int FINISH_NT = 256;   // 256 x 47 registers: fits next to a resident head CTA (see TC_MAX_REGS)
 constexpr int FINISH_SMEM_NC = 1024;
 
 __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int nc, NmsWs ws, int *__restrict__ out_counts,

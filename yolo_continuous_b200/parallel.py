@@ -50,11 +50,18 @@ class DetectionGather:
         self.cuda = torch.device(device).type == "cuda"
         self.stream = torch.cuda.Stream(device=device) if self.cuda else None
 
-    def gather_async(self, msg):
+    def gather_async(self, msg, stream=None):
+        """stream: run the collective in order on this stream (e.g. PostBackbone.tail_stream, which produced
+        `msg`) instead of this object's own side stream behind an event on the current stream."""
         assert msg.numel() == self.msg_bytes and msg.dtype == torch.uint8
         self.slot = (self.slot + 1) % len(self.out)
         dst = self.out[self.slot]
-        if self.cuda:
+        if self.cuda and stream is not None:
+            self.last_stream = stream
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(dst, msg, group=self.group)
+        elif self.cuda:
+            self.last_stream = self.stream
             ev = torch.cuda.Event()
             ev.record()
             with torch.cuda.stream(self.stream):
@@ -66,7 +73,7 @@ class DetectionGather:
 
     def wait(self):
         if self.cuda:
-            torch.cuda.current_stream().wait_stream(self.stream)
+            torch.cuda.current_stream().wait_stream(getattr(self, "last_stream", self.stream))
 
     def unpack(self, slot, bs, hdr_ints, gather_rows):
         """-> list over ranks of (counts [bs], total, rows [min(total, gather_rows), 7]) views (no copy)."""

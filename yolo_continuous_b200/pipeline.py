@@ -5,7 +5,10 @@ backbone (detect.py:227-234): head (conv + implicit + decode) -> threshold/compa
 NMS -> letterbox undo.  Two entry points:
 
 * run_device(features): inputs already on the device; results stay on the device.  The whole step
-  (1 head kernel + the NMS kernels) can be replayed as one CUDA graph.
+  (1 head kernel + the NMS kernels) can be replayed as one CUDA graph.  With overlap=True the NMS kernels of a
+  batch run on a second stream (`tail_stream`) next to the head kernel of the following batch: the persistent
+  head kernel leaves a quarter of each SM's registers and ~19 KB of its shared memory free for them, workspaces and
+  outputs are double-buffered, and the results of a call are complete once `done_event` has fired.
 * run_host(features_host): the user-facing call with HOST buffers -- pinned host feature maps are
   copied to the device, the step runs, and the per-image detection arrays are copied back.
 """
@@ -20,7 +23,7 @@ from . import _lib
 class PostBackbone:
     def __init__(self, head, bs, shapes, dtype=torch.bfloat16, input_shape=(640, 640), image_shape=(640, 640),
                  letterbox_image=True, conf_thres=0.25, nms_thres=0.45, device="cuda:0", use_graph=True,
-                 spec_rows=65536, fused=True, double_buffer=False):
+                 spec_rows=65536, fused=True, double_buffer=False, overlap=False):
         self.head, self.bs, self.shapes = head, bs, [tuple(s) for s in shapes]
         self.device = torch.device(device)
         self.dtype = dtype
@@ -39,15 +42,20 @@ class PostBackbone:
             # rows) can be sent as a single all-gather / D2H copy.  Two of them when double-buffered (the
             # multi-GPU exchange of step i overlaps step i+1).
             self.hdr_ints = (2 * bs + 1 + 3) // 4 * 4
-            self.n_bufs = 2 if double_buffer else 1
+            self.overlap = bool(overlap)
+            self.n_bufs = 2 if (double_buffer or overlap) else 1
             self.msgs = [torch.empty((self.hdr_ints * 4 + bs * self.rows * 28,), dtype=torch.uint8, device=dev)
                          for _ in range(self.n_bufs)]
             self.metas = [m[:self.hdr_ints * 4].view(torch.int32)[:2 * bs + 1] for m in self.msgs]
             self.rows_bufs = [m[self.hdr_ints * 4:].view(torch.float32).view(bs * self.rows, 7) for m in self.msgs]
             self.cur = 0
-            self.out_idx = torch.empty((bs * self.rows,), dtype=torch.int32, device=dev)
-            self.ws = torch.empty(_lib.lib.yc_nms_workspace_bytes(bs, self.rows, self.nc) + 1024, dtype=torch.uint8,
-                                  device=dev)
+            n_ws = 2 if overlap else 1
+            self.out_idxs = [torch.empty((bs * self.rows,), dtype=torch.int32, device=dev) for _ in range(n_ws)]
+            self.wss = [torch.empty(_lib.lib.yc_nms_workspace_bytes(bs, self.rows, self.nc) + 1024, dtype=torch.uint8,
+                                    device=dev) for _ in range(n_ws)]
+            self.tail_stream = torch.cuda.Stream(device=dev) if overlap else None
+            self.ev_head = [torch.cuda.Event() for _ in range(n_ws)]
+            self.ev_tail = [torch.cuda.Event() for _ in range(n_ws)]
             hw = np.asarray(image_shape, dtype=np.int32).reshape(-1, 2)
             self.image_hw = torch.from_numpy(np.ascontiguousarray(hw)).to(dev)
             self.x_host = [torch.empty(t.shape, dtype=dtype).pin_memory() for t in self.x_dev]
@@ -83,9 +91,36 @@ class PostBackbone:
         # (bucket, per-segment NMS, finish); otherwise head kernel (writes z) + threshold/compaction + the same 3.
         # (memsets are not kernels)
         self.fused = fused and dtype == torch.bfloat16
+        if self.overlap and not self.fused:
+            raise _lib.YcError("overlap=True needs the fused step (bf16 feature maps)")
         self.kernels_per_step = 4 if self.fused else 5
         self._graphs = {}
-        self.use_graph = use_graph
+        self.use_graph = use_graph and not self.overlap
+        if self.overlap:
+            with torch.cuda.device(dev):
+                for i in range(2):
+                    _lib.check(_lib.lib.yc_nms_workspace_reset(C.byref(p), self.wss[i].data_ptr(), self.wss[i].numel(),
+                                                               C.c_void_p(self.tail_stream.cuda_stream)),
+                               "yc_nms_workspace_reset")
+                    self.ev_tail[i].record(self.tail_stream)
+
+    @property
+    def ws(self):
+        return self.wss[self.cur if self.overlap else 0]
+
+    @property
+    def out_idx(self):
+        return self.out_idxs[self.cur if self.overlap else 0]
+
+    @property
+    def done_event(self):
+        """Fires when the results of the latest run_device call are complete (overlap mode)."""
+        return self.ev_tail[self.cur]
+
+    def wait(self):
+        """Make the current stream wait for the results of the latest run_device call (no-op without overlap)."""
+        if self.overlap:
+            torch.cuda.current_stream(self.device).wait_event(self.ev_tail[self.cur])
 
     @property
     def meta(self):
@@ -100,13 +135,43 @@ class PostBackbone:
         return self.msgs[self.cur][:self.hdr_ints * 4 + gather_rows * 28]
 
     # ---- device path -----------------------------------------------------------------------
-    def _launch(self, features):
+    def _launch(self, features, head_events=None):
         for i, x in enumerate(features):
             if x.dtype != self.dtype or tuple(x.shape) != tuple(self.x_dev[i].shape) or not x.is_contiguous():
                 raise _lib.YcError(f"level {i}: expected contiguous {tuple(self.x_dev[i].shape)} {self.dtype}")
             self.desc.level[i].x = x.data_ptr()
         s = _lib.stream_ptr(self.device)
         m = self.meta.data_ptr()
+        if self.fused and (self.overlap or head_events is not None):
+            # head and NMS halves as two calls: the NMS half on the tail stream (overlap) and/or the head half
+            # bracketed by the caller's events (bench.py's per-kernel timing)
+            main = torch.cuda.current_stream(self.device)
+            c = self.cur
+            if self.overlap:
+                main.wait_event(self.ev_tail[c])    # the tail that used this workspace/output two calls ago
+            if head_events is not None:
+                head_events[0].record(main)
+            # overlap: the workspace counters were cleared on the tail stream (at construction / behind the NMS
+            # kernels that used them last), so the head stream carries nothing but the head kernel
+            head_fn = _lib.lib.yc_detect_fused_head_noreset if self.overlap else _lib.lib.yc_detect_fused_head
+            _lib.check(head_fn(C.byref(self.desc), C.byref(self.nms_params), self.ws.data_ptr(), self.ws.numel(), s),
+                       "yc_detect_fused_head")
+            if head_events is not None:
+                head_events[1].record(main)
+            tail = main
+            if self.overlap:
+                self.ev_head[c].record(main)
+                tail = self.tail_stream
+                tail.wait_event(self.ev_head[c])
+            _lib.check(_lib.lib.yc_nms_from_candidates(C.byref(self.nms_params), self.ws.data_ptr(), self.ws.numel(),
+                                                       self.out_rows.data_ptr(), self.out_idx.data_ptr(), m,
+                                                       m + 4 * self.bs, C.c_void_p(tail.cuda_stream)),
+                       "yc_nms_from_candidates")
+            if self.overlap:
+                _lib.check(_lib.lib.yc_nms_workspace_reset(C.byref(self.nms_params), self.ws.data_ptr(), self.ws.numel(),
+                                                           C.c_void_p(tail.cuda_stream)), "yc_nms_workspace_reset")
+                self.ev_tail[c].record(tail)
+            return
         if self.fused:
             rc = _lib.lib.yc_detect_fused(C.byref(self.desc), C.byref(self.nms_params), self.ws.data_ptr(),
                                           self.ws.numel(), self.out_rows.data_ptr(), self.out_idx.data_ptr(),
@@ -120,15 +185,16 @@ class PostBackbone:
                                            self.ws.numel(), self.out_rows.data_ptr(), self.out_idx.data_ptr(),
                                            m, m + 4 * self.bs, s), "yc_nms_batched")
 
-    def run_device(self, features):
+    def run_device(self, features, head_events=None):
         """features: list of [bs, ch_i, H_i, W_i] device tensors.  Returns device views
-        (rows [bs*rows,7] capacity, idx, counts [bs], offsets [bs+1])."""
+        (rows [bs*rows,7] capacity, idx, counts [bs], offsets [bs+1]); with overlap=True they are complete once
+        `done_event` has fired (`wait()` orders the current stream behind it)."""
         with torch.cuda.device(self.device):
             if self.n_bufs > 1:
                 self.cur ^= 1
             ptrs = tuple(x.data_ptr() for x in features) + (self.cur,)
-            if not self.use_graph:
-                self._launch(features)
+            if not self.use_graph or head_events is not None:
+                self._launch(features, head_events)
             else:
                 g = self._graphs.get(ptrs)
                 if g is None:
@@ -153,6 +219,7 @@ class PostBackbone:
             for d_, h_ in zip(self.x_dev, src):
                 d_.copy_(h_, non_blocking=True)
             rows, _, _, _ = self.run_device(self.x_dev)
+            self.wait()
             self.meta_host.copy_(self.meta, non_blocking=True)
             spec = self.spec_rows
             self.rows_host[:spec].copy_(rows[:spec], non_blocking=True)
