@@ -79,6 +79,9 @@ typedef struct yc_head_level {
     int32_t K, H, W;
     float stride;                         /* IDetect.stride[i] */
     float anchor_wh[YC_MAX_ANCHORS * 2];  /* anchor_grid[i] in pixels, nets/idetect.py:18-20 */
+    float stride_y;                       /* multiplier of the y coordinate; 0 = same as `stride`.  The plain Detect
+                                             head + decode_box (detect.py:29-87, normalised boxes) is this decode with
+                                             stride = 1/W, stride_y = 1/H and anchor_wh = anchor / image_size */
 } yc_head_level;
 
 typedef struct yc_head_desc {
@@ -161,6 +164,32 @@ YC_API int yc_nms_single(const float *boxes, const float *scores, int n, double 
                   int32_t *keep, int32_t *keep_count_dev, yc_stream_t stream);
 
 /* utils/bbox.py:62-72 box_iou and :29-59 cvt_bbox on device. */
+/* ------------------------------------------------------------------------------------------
+ * The steps either side of the model.
+ * yc_letterbox_batch replaces prepare_test_image (detect.py:16-26) + LetterBox.__call__ without scale_fill
+ * (image_enhance/letter_box.py:27-60) for a batch: cv2.resize INTER_LINEAR (8-bit fixed point, bit exact),
+ * constant border `pad_value` (114), /255, HWC -> CHW, channel order kept (BGR as cv2.imread gives it).
+ * `imgs` is a DEVICE array of bs descriptors; src images are uint8 HWC with 3 channels on the device.
+ * rs_w/rs_h = int(round(w*r)), int(round(h*r)); top/left = int(round(dh-0.1)), int(round(dw-0.1)) as the reference
+ * computes them on the host.  out: [bs, 3, out_h, out_w] of `out_dtype` (YC_F32 / YC_BF16).
+ */
+typedef struct yc_letterbox_image {
+    const uint8_t *src;
+    int32_t src_h, src_w, src_pitch; /* pitch in bytes */
+    int32_t rs_h, rs_w;              /* size after the resize */
+    int32_t top, left;               /* where the resized image starts in the output */
+    int32_t pad_value;               /* 114 */
+} yc_letterbox_image;
+YC_API int yc_letterbox_batch(const yc_letterbox_image *imgs, int bs, int out_h, int out_w, int out_dtype, void *out,
+                       yc_stream_t stream);
+
+/* Formatting loop of predict (detect.py:236-258) for every detection of a batch: rows [total,7]
+ * (y1,x1,y2,x2,obj,class_conf,class) and offsets [bs+1] as yc_nms_batched / yc_detect_fused leave them ->
+ * box_xyxy int32 [total,4] = (max(0,floor x1), max(0,floor y1), min(W,floor x2), min(H,floor y2)),
+ * conf = obj*class_conf, label = int(class).  image_hw as in yc_nms_params. */
+YC_API int yc_format_detections(const float *rows, const int32_t *offsets, int bs, const int32_t *image_hw,
+                         int image_hw_stride, int32_t *box_xyxy, float *conf, int32_t *label, yc_stream_t stream);
+
 YC_API int yc_box_iou(const float *b1, int n, const float *b2, int m, float *out, yc_stream_t stream);
 YC_API int yc_cvt_bbox(const float *in, int n, int flag, float *out, yc_stream_t stream);
 

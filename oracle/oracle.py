@@ -184,3 +184,75 @@ def cvt_bbox(bbox, flag):
     if rc != 0:
         raise Exception()
     return out
+
+
+# ---- preprocessing / formatting either side of the model ---------------------------------
+def letterbox_geometry(h, w, new_shape=(640, 640)):
+    """Scalar part of LetterBox.__call__ without scale_fill (image_enhance/letter_box.py:38-58):
+    -> (rs_w, rs_h, top, bottom, left, right, ratio, dw, dh)."""
+    ratio = (new_shape[0] / w, new_shape[1] / h)
+    r = min(ratio)
+    rs_w, rs_h = int(round(w * r)), int(round(h * r))
+    dw, dh = (new_shape[0] - rs_w) / 2, (new_shape[1] - rs_h) / 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return rs_w, rs_h, top, bottom, left, right, r, dw, dh
+
+
+def resize_linear_u8(src, dw, dh):
+    """cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR) for uint8 HWC images: OpenCV's fixed-point
+    bilinear (third-party, opencv-python 4.13, imgproc/resize.cpp: 11-bit coefficients, int32 horizontal pass,
+    vertical pass ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2) >> 2; call site image_enhance/letter_box.py:53)."""
+    sh, sw = src.shape[:2]
+
+    def coefs(ssize, dsize, clamp):
+        scale = 1.0 / (dsize / ssize)
+        idx, a = np.zeros(dsize, np.int64), np.zeros((dsize, 2), np.int64)
+        for d in range(dsize):
+            f = np.float32((d + 0.5) * scale - 0.5)
+            s = int(np.floor(f))
+            f = np.float32(f - np.float32(s))
+            if clamp:
+                if s < 0:
+                    f, s = np.float32(0), 0
+                if s >= ssize - 1:
+                    f, s = np.float32(0), ssize - 1
+            idx[d] = s
+            a[d, 0] = int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048))))
+            a[d, 1] = int(np.rint(np.float32(f * np.float32(2048))))
+        return idx, a
+
+    xi, xa = coefs(sw, dw, True)
+    yi, ya = coefs(sh, dh, False)
+    s = src.astype(np.int64)
+    x1 = np.minimum(xi + 1, sw - 1)
+    rows = s[:, xi] * xa[:, 0][None, :, None] + s[:, x1] * xa[:, 1][None, :, None]
+    y0, y1 = np.clip(yi, 0, sh - 1), np.clip(yi + 1, 0, sh - 1)
+    b0, b1 = ya[:, 0][:, None, None], ya[:, 1][:, None, None]
+    out = (((b0 * (rows[y0] >> 4)) >> 16) + ((b1 * (rows[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def prepare_test_image(image, target_size, color=114):
+    """prepare_test_image (detect.py:16-26) on a decoded uint8 HWC image: LetterBox(target_size, scale_fill_prob=0)
+    -> float32 / 255 -> CHW -> [1,3,H,W]."""
+    h, w = image.shape[:2]
+    rs_w, rs_h, top, bottom, left, right, _, _, _ = letterbox_geometry(h, w, target_size)
+    img = resize_linear_u8(image, rs_w, rs_h)   # the reference skips the call when the size is unchanged: identity
+    out = np.full((top + rs_h + bottom, left + rs_w + right, 3), color, np.uint8)
+    out[top:top + rs_h, left:left + rs_w] = img
+    return np.expand_dims(np.transpose(np.array(out, dtype='float32') / 255., (2, 0, 1)), 0)
+
+
+def format_detections(rows, image_shape):
+    """The formatting loop of predict (detect.py:236-258) for one image: rows [n,7] (y1,x1,y2,x2,obj,cls_conf,cls)
+    -> (box_xyxy int32 [n,4], conf float32 [n], label int32 [n])."""
+    rows = np.asarray(rows, np.float32).reshape(-1, 7)
+    label = np.array(rows[:, 6], dtype='int32')
+    conf = rows[:, 4] * rows[:, 5]
+    box = np.empty((rows.shape[0], 4), np.int32)
+    for i in range(rows.shape[0]):
+        y1, x1, y2, x2 = rows[i, :4]
+        box[i] = [max(0, np.floor(x1).astype('int32')), max(0, np.floor(y1).astype('int32')),
+                  min(image_shape[1], np.floor(x2).astype('int32')), min(image_shape[0], np.floor(y2).astype('int32'))]
+    return box, conf, label

@@ -220,6 +220,19 @@ def main():
     va["anchors"], va["mask"], va["nc"], va["image_size"] = anchors, np.asarray(mask), np.int64(nc), np.asarray([64, 64])
     np.savez_compressed(os.path.join(HERE, "variant_a.npz"), **va)
 
+    # --- 8f: prepare_test_image (detect.py:16-26) on synthetic images (cv2.imread replaced by an in-memory image) ---
+    from image_enhance.letter_box import LetterBox
+    rng = np.random.default_rng(21)
+    for name, (h, w), target in (("letterbox_wide", (48, 77), (64, 64)), ("letterbox_tall_up", (23, 14), (64, 64)),
+                                 ("letterbox_same", (64, 64), (64, 64)), ("letterbox_down", (300, 171), (96, 96))):
+        # smooth-ish content plus noise so that interpolation errors would show
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = (127 + 100 * np.sin(xx / 5.0)[..., None] * np.cos(yy / 7.0)[..., None] * np.ones(3)).astype(np.float64)
+        img = np.clip(base + rng.integers(-30, 31, (h, w, 3)), 0, 255).astype(np.uint8)
+        image_data, _ = LetterBox(target, scale_fill_prob=0)(img, np.zeros((0, 4)))
+        data = np.expand_dims(np.transpose((np.array(image_data, dtype='float32') / 255.), (2, 0, 1)), 0)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), image=img, target=np.asarray(target), data=data)
+
     # --- a9-a11: NMS ---------------------------------------------------------------------------
     nms_case("nms_clustered_lb", clustered_prediction(2, 320, 80, 7), 80, 0.25, 0.45, (640, 640), (512, 773), True)
     nms_case("nms_clustered_nolb", clustered_prediction(2, 320, 80, 8), 80, 0.3, 0.3, (640, 640), (480, 640), False)

@@ -160,6 +160,35 @@ def test_decode_box_variant_a_vs_golden():
 NMS_FIXTURES = ["nms_clustered_lb", "nms_clustered_nolb", "nms_lowconf", "nms_with_none", "nms_nc1", "nms_thr_round"]
 
 
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, RTOL_F32), (torch.bfloat16, RTOL_BF16)])
+def test_detect_forward_decoded_vs_golden(dtype, rtol):
+    """Plain Detect head with the conv and Variant A's decode fused (nets/detect.py + detect.py:29-87) against the
+    reference's own Detect.forward -> decode_box outputs."""
+    from yolo_continuous_b200.nets import Detect
+    fx = load("variant_a")
+    nc, anchors, mask = int(fx["nc"]), fx["anchors"], fx["mask"].tolist()
+    det = Detect(nc, [[0] * 6] * 3, (8, 16, 32)).to(DEV).eval()
+    det.load_state_dict({k[4:].replace("__", "."): torch.from_numpy(v) for k, v in fx.items() if k.startswith("sd__")})
+    xs = [torch.from_numpy(fx[f"x{i}"]).to(DEV) for i in range(3)]
+    want = [fx[f"out{i}"] for i in range(3)]
+    if dtype == torch.bfloat16:
+        # bf16 maps: expected values = the oracle's decode_box on fp32 convolutions of the same bf16-rounded inputs
+        # and bf16-rounded weights (bf16 maps select the bf16 weight copy on every kernel path; the fixture's weights
+        # are large, std 0.3, so the weight rounding is visible at 1e-3)
+        xs = [x.to(torch.bfloat16) for x in xs]
+        convs = []
+        for i in range(3):
+            w = torch.from_numpy(fx[f"sd__yolo_head_P{5 - i}__weight"]).to(torch.bfloat16).float()
+            convs.append(torch.nn.functional.conv2d(xs[2 - i].float().cpu(), w,
+                                                    torch.from_numpy(fx[f"sd__yolo_head_P{5 - i}__bias"])).numpy())
+        want = orc.decode_box(convs, anchors, mask, nc, tuple(int(v) for v in fx["image_size"]))
+    outs = det.forward_decoded(xs, anchors, mask, tuple(int(v) for v in fx["image_size"]))
+    assert outs[0]._base is not None and outs[0]._base.shape[1] == sum(o.shape[1] for o in outs)
+    for i in range(3):
+        scale = np.ones((1, 1, nc + 5), np.float32)   # normalised boxes: |a-b| <= rtol * max(|ref|, 1)
+        assert_close_scaled(outs[i].cpu().numpy(), want[i], scale, rtol, f"detect {dtype} level {i}")
+
+
 @pytest.mark.parametrize("name", NMS_FIXTURES)
 def test_nms_vs_golden_bit_exact(name):
     from yolo_continuous_b200 import detect
@@ -463,6 +492,53 @@ def test_fused_step_equals_two_call_path(nc, conf, iou, bs, shapes):
         assert (out[b] is None) == (len(want) == 0)
         if out[b] is not None:
             assert np.array_equal(out[b], want)
+
+
+@pytest.mark.parametrize("name", ["letterbox_wide", "letterbox_tall_up", "letterbox_same", "letterbox_down"])
+def test_letterbox_kernel_vs_golden_bit_exact(name):
+    """Device letterbox (resize + pad + /255 + CHW) against the reference's prepare_test_image output, bit for bit;
+    bf16 output = that result rounded to bf16."""
+    from yolo_continuous_b200.image_enhance import LetterBox, letterbox_batch
+    fx = load(name)
+    target = tuple(int(v) for v in fx["target"])
+    x, geos = letterbox_batch([fx["image"]], target, torch.float32, DEV)
+    assert np.array_equal(x.cpu().numpy(), fx["data"])
+    xb, _ = letterbox_batch([torch.from_numpy(fx["image"]).to(DEV)], target, torch.bfloat16, DEV)
+    assert torch.equal(xb.cpu(), torch.from_numpy(fx["data"]).to(torch.bfloat16))
+    # class form: uint8 HWC out, labels shifted as image_enhance/letter_box.py:60-62
+    img8, tgt = LetterBox(target, scale_fill_prob=0)(fx["image"], np.array([[1.0, 2.0, 10.0, 12.0]]))
+    assert np.array_equal(np.transpose(img8.astype(np.float32) / 255.0, (2, 0, 1))[None], fx["data"])
+    g = geos[0]
+    assert np.allclose(tgt, [[1 * g["ratio"][0] + g["dw"], 2 * g["ratio"][1] + g["dh"], 10 * g["ratio"][0] + g["dw"],
+                             12 * g["ratio"][1] + g["dh"]]])
+
+
+def test_letterbox_batch_mixed_sizes_vs_oracle():
+    """A batch of images of different sizes and aspect ratios (incl. extreme up- and down-scaling) at 640x640."""
+    from yolo_continuous_b200.image_enhance import letterbox_batch
+    rng = np.random.default_rng(3)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in ((512, 773), (37, 53), (1080, 1920), (640, 640),
+                                                                          (641, 479), (2, 3))]
+    x, _ = letterbox_batch(imgs, (640, 640), torch.float32, DEV)
+    for i, img in enumerate(imgs):
+        assert np.array_equal(x[i:i + 1].cpu().numpy(), orc.prepare_test_image(img, (640, 640))), f"image {i}"
+
+
+def test_format_detections_vs_oracle():
+    """Formatting loop of predict (detect.py:236-258) on the device for a batch with an empty image."""
+    from yolo_continuous_b200 import detect
+    rng = np.random.default_rng(9)
+    counts = [17, 0, 40]
+    hw = np.array([[480, 640], [300, 500], [512, 773]], np.int32)
+    rows = np.concatenate([np.concatenate([rng.uniform(-20, 800, (n, 4)), rng.uniform(0, 1, (n, 2)),
+                                           rng.integers(0, 80, (n, 1))], 1) for n in counts]).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    box, conf, label = detect.format_detections(torch.from_numpy(rows).to(DEV), torch.from_numpy(off).to(DEV), hw)
+    for b, n in enumerate(counts):
+        wb, wc, wl = orc.format_detections(rows[off[b]:off[b + 1]], hw[b])
+        assert np.array_equal(box[off[b]:off[b + 1]].cpu().numpy(), wb)
+        assert np.array_equal(conf[off[b]:off[b + 1]].cpu().numpy(), wc)
+        assert np.array_equal(label[off[b]:off[b + 1]].cpu().numpy(), wl)
 
 
 def test_overlapped_pipeline_equals_serial():

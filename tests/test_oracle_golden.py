@@ -106,3 +106,26 @@ def test_torch_port_matches_reference_bit_exact():
         got = np.concatenate(rows, 0) if rows else np.zeros((0, 7), np.float32)
         assert np.array_equal(got, fx["rows"].astype(np.float32))
         assert [0 if o is None else len(o) for o in out] == fx["counts"].tolist()
+
+
+LETTERBOX_FIXTURES = ["letterbox_wide", "letterbox_tall_up", "letterbox_same", "letterbox_down"]
+
+
+@pytest.mark.parametrize("name", LETTERBOX_FIXTURES)
+def test_oracle_prepare_test_image_bit_exact(name):
+    """prepare_test_image (detect.py:16-26: LetterBox + cv2.resize INTER_LINEAR + /255 + CHW) restated without
+    OpenCV, bit for bit against the reference's own output."""
+    fx = load(name)
+    got = orc.prepare_test_image(fx["image"], tuple(int(v) for v in fx["target"]))
+    assert got.dtype == np.float32 and got.shape == fx["data"].shape
+    assert np.array_equal(got, fx["data"])
+
+
+def test_oracle_format_detections():
+    """Formatting loop of predict (detect.py:236-258): floor, clamp, obj*cls_conf, int label."""
+    rows = np.array([[-3.7, 10.2, 50.9, 700.5, 0.9, 0.5, 3.0],
+                     [12.0, -0.4, 480.0, 639.99, 0.25, 0.25, 79.0],
+                     [470.5, 630.5, 490.0, 650.0, 1.0, 0.3, 0.0]], np.float32)
+    box, conf, label = orc.format_detections(rows, (480, 640))
+    assert box.tolist() == [[10, 0, 640, 50], [0, 12, 639, 480], [630, 470, 640, 480]]
+    assert np.array_equal(conf, rows[:, 4] * rows[:, 5]) and label.tolist() == [3, 79, 0]

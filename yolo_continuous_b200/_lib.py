@@ -16,7 +16,8 @@ YC_ERR_UNSUPPORTED = -2
 class HeadLevel(C.Structure):
     _fields_ = [("x", C.c_void_p), ("blob", C.c_void_p), ("raw", C.c_void_p),
                 ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("stride", C.c_float), ("anchor_wh", C.c_float * (YC_MAX_ANCHORS * 2))]
+                ("stride", C.c_float), ("anchor_wh", C.c_float * (YC_MAX_ANCHORS * 2)),
+                ("stride_y", C.c_float)]
 
 
 class HeadDesc(C.Structure):
@@ -39,7 +40,8 @@ class NmsParams(C.Structure):
 EXPORTS = ["yc_last_error", "yc_version", "yc_device_check", "yc_head_pack_bytes", "yc_head_pack",
            "yc_head_forward", "yc_decode_box", "yc_nms_workspace_bytes", "yc_nms_batched",
            "yc_nms_single", "yc_box_iou", "yc_cvt_bbox", "yc_detect_fused",
-           "yc_detect_fused_head", "yc_nms_from_candidates", "yc_nms_workspace_reset", "yc_detect_fused_head_noreset"]
+           "yc_detect_fused_head", "yc_nms_from_candidates", "yc_nms_workspace_reset", "yc_detect_fused_head_noreset",
+           "yc_letterbox_batch", "yc_format_detections"]
 
 
 def _load():
@@ -69,6 +71,9 @@ def _load():
     lib.yc_nms_workspace_reset.argtypes = [C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.yc_nms_from_candidates.argtypes = [C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.yc_letterbox_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.yc_format_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
     lib.yc_nms_single.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_box_iou.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

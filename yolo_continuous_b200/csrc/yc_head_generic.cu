@@ -86,7 +86,7 @@ struct GenericLevel {
     float *z;           // base of z, or null
     int K, HW, nx;
     int row_off;        // first z row of this level
-    float stride;
+    float stride, stride_y;
     float anchor_wh[YC_MAX_ANCHORS * 2];
 };
 
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) head_generic_kernel(GenericLevel L, int n
             if (decode) {
                 float s = sigmoidf_fast(t);
                 if (o == 0) s = decode_xy(s, (float)(p % L.nx), L.stride);
-                else if (o == 1) s = decode_xy(s, (float)(p / L.nx), L.stride);
+                else if (o == 1) s = decode_xy(s, (float)(p / L.nx), L.stride_y);
                 else if (o < 4) s = decode_wh(s, L.anchor_wh[a * 2 + (o - 2)]);
                 L.z[((size_t)b * rows_total + L.row_off + (size_t)a * L.HW + p) * no + o] = s;
             }
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) head_generic_kernel(GenericLevel L, int n
 // ------------------------------------------------------------------------------------------------
 // IBin decode (reference nets/ibin.py:56-72, losses/sigmoid_bin.py:49-63): one thread per output element.
 __global__ void __launch_bounds__(256) ibin_decode_kernel(const float *__restrict__ raw, int bs, int na, int HW, int nx,
-                                                          int no_in, int bin_count, float stride, float step,
+                                                          int no_in, int bin_count, float stride, float stride_y, float step,
                                                           const float *__restrict__ bins, float a_w0, float a_h0,
                                                           float a_w1, float a_h1, float a_w2, float a_h2, float a_w3,
                                                           float a_h3, float *__restrict__ z, int rows_total, int row_off)
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) ibin_decode_kernel(const float *__restric
     const float *q = raw + r * no_in;
     float v;
     if (j < 2) {
-        v = decode_xy(sigmoidf_fast(q[j]), j == 0 ? (float)(p % nx) : (float)(p / nx), stride);
+        v = j == 0 ? decode_xy(sigmoidf_fast(q[j]), (float)(p % nx), stride) : decode_xy(sigmoidf_fast(q[j]), (float)(p / nx), stride_y);
     } else if (j < 4) {
         const float *g = q + 2 + (j - 2) * len;
         float reg = __fmul_rn(sigmoidf_fast(g[0]), 2.0f);
@@ -252,6 +252,7 @@ int launch_head_generic(const yc_head_desc *d, int rows_total, const int *row_of
         L.K = lv.K; L.HW = HW; L.nx = lv.W;
         L.row_off = row_off[i];
         L.stride = lv.stride;
+        L.stride_y = lv.stride_y > 0.f ? lv.stride_y : lv.stride;
         for (int j = 0; j < YC_MAX_ANCHORS * 2; ++j) L.anchor_wh[j] = lv.anchor_wh[j];
         const int decode = d->kind == YC_HEAD_IDETECT ? 1 : 0;
         if (d->kind != YC_HEAD_IDETECT)
@@ -266,7 +267,7 @@ int launch_head_generic(const yc_head_desc *d, int rows_total, const int *row_of
             const size_t total = (size_t)d->bs * d->na * HW * no_out;
             const float *a = lv.anchor_wh;
             ibin_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-                lv.raw, d->bs, d->na, HW, lv.W, d->no, d->bin_count, lv.stride, (float)(4.0 / (double)d->bin_count), d->bins, a[0], a[1], a[2], a[3], a[4],
+                lv.raw, d->bs, d->na, HW, lv.W, d->no, d->bin_count, lv.stride, lv.stride_y > 0.f ? lv.stride_y : lv.stride, (float)(4.0 / (double)d->bin_count), d->bins, a[0], a[1], a[2], a[3], a[4],
                 a[5], a[6], a[7], d->z, rows_total, row_off[i]);
         }
     }

@@ -224,15 +224,15 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (L.raw) {
                 if (lane == 0) bulk_wait_read0(); // previous store from this slab has been read out
                 __syncwarp();
-                epi_row<true>(taddr, no, sb, slab + lane * no, gx, gy, L.stride, aw, ah);
+                epi_row<true>(taddr, no, sb, slab + lane * no, gx, gy, L.stride, L.stride_y, aw, ah);
                 if (nv > 0)
                     slab_store(L.raw + (((size_t)tc.b * P.na_real + ar) * L.HW + prow0) * no, slab, nv, no, lane);
             }
             if (P.write_z) {
                 if (lane == 0) bulk_wait_read0();
                 __syncwarp();
-                if (P.ibin) epi_row_ibin(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, aw, ah, P);
-                else epi_row<false>(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, aw, ah);
+                if (P.ibin) epi_row_ibin(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, L.stride_y, aw, ah, P);
+                else epi_row<false>(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, L.stride_y, aw, ah);
             }
             // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA warp
             tc_fence_before();
@@ -373,6 +373,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         L.tile_begin = tiles;
         L.row_off = row_off[i];
         L.stride = lv.stride;
+        L.stride_y = lv.stride_y > 0.f ? lv.stride_y : lv.stride;
         for (int j = 0; j < YC_MAX_ANCHORS * 2; ++j) L.anchor_wh[j] = lv.anchor_wh[j];
         tiles += d->bs * L.tiles_per_img * n_groups;
         {   // A: X [bs, K, HW] bf16, box {64 px, 64 k, 1}

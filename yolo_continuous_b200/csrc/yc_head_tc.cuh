@@ -44,7 +44,7 @@ struct TcLevel {
     int tiles_per_img;  // ceil(HW / 128)
     int tile_begin;     // first tile id of this level in schedule order
     int row_off;        // first z row of this level
-    float stride;
+    float stride, stride_y;
     float anchor_wh[YC_MAX_ANCHORS * 2];
 };
 
@@ -104,7 +104,7 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams &P, int t) { retu
 //   !RAW:  slab[o] = decode(sigmoid(t))    (z row; o<2 xy, o<4 wh: nets/idetect.py:40-42)
 template <int W, bool RAW>
 __device__ __forceinline__ void epi_chunk(uint32_t taddr, int c0, const float2 *__restrict__ sb, float *__restrict__ srow,
-                                          float gx, float gy, float stride, float aw, float ah)
+                                          float gx, float gy, float stride, float stride_y, float aw, float ah)
 {
     uint32_t v[W];
     TmemLd<W>::ld(taddr + (uint32_t)c0, v);
@@ -120,7 +120,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, int c0, const float2 *
             r = sigmoidf_fast(t);
             const int o = c0 + j;
             if (o == 0) r = decode_xy(r, gx, stride);
-            else if (o == 1) r = decode_xy(r, gy, stride);
+            else if (o == 1) r = decode_xy(r, gy, stride_y);
             else if (o == 2) r = decode_wh(r, aw);
             else if (o == 3) r = decode_wh(r, ah);
         }
@@ -130,15 +130,15 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, int c0, const float2 *
 
 template <bool RAW>
 __device__ __forceinline__ void epi_row(uint32_t taddr, int no, const float2 *__restrict__ sb, float *__restrict__ srow,
-                                        float gx, float gy, float stride, float aw, float ah)
+                                        float gx, float gy, float stride, float stride_y, float aw, float ah)
 {
     int c0 = 0;
-    for (; c0 + 16 <= no; c0 += 16) epi_chunk<16, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah);
+    for (; c0 + 16 <= no; c0 += 16) epi_chunk<16, RAW>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah);
     const int rem = no - c0;
-    if (rem & 8) { epi_chunk<8, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 8; }
-    if (rem & 4) { epi_chunk<4, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 4; }
-    if (rem & 2) { epi_chunk<2, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); c0 += 2; }
-    if (rem & 1) { epi_chunk<1, RAW>(taddr, c0, sb, srow, gx, gy, stride, aw, ah); }
+    if (rem & 8) { epi_chunk<8, RAW>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); c0 += 8; }
+    if (rem & 4) { epi_chunk<4, RAW>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); c0 += 4; }
+    if (rem & 2) { epi_chunk<2, RAW>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); c0 += 2; }
+    if (rem & 1) { epi_chunk<1, RAW>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); }
 }
 
 
@@ -147,7 +147,7 @@ __device__ __forceinline__ void epi_row(uint32_t taddr, int no, const float2 *__
 // sigmoided bins takes the first maximum.  Same operation order as ibin_decode_kernel (generic path).
 template <int W>
 __device__ __forceinline__ void ibin_chunk(uint32_t taddr, int c0, const float2 *__restrict__ sb, float *__restrict__ srow,
-                                           float gx, float gy, float stride, int len, float &reg_w, float &reg_h, float &best_w,
+                                           float gx, float gy, float stride, float stride_y, int len, float &reg_w, float &reg_h, float &best_w,
                                            float &best_h, int &idx_w, int &idx_h)
 {
     uint32_t v[W];
@@ -159,7 +159,7 @@ __device__ __forceinline__ void ibin_chunk(uint32_t taddr, int c0, const float2 
         const float2 s_b = __ldg(sb + o);
         const float sg = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
         if (o < 2) {
-            srow[o] = decode_xy(sg, o == 0 ? gx : gy, stride);
+            srow[o] = o == 0 ? decode_xy(sg, gx, stride) : decode_xy(sg, gy, stride_y);
         } else if (o < 2 + 2 * len) {
             if (o < 2 + len) {
                 const int k = o - 2;
@@ -177,18 +177,18 @@ __device__ __forceinline__ void ibin_chunk(uint32_t taddr, int c0, const float2 
 }
 
 __device__ __forceinline__ void epi_row_ibin(uint32_t taddr, int no, const float2 *__restrict__ sb, float *__restrict__ srow,
-                                             float gx, float gy, float stride, float aw, float ah, const TcParams &P)
+                                             float gx, float gy, float stride, float stride_y, float aw, float ah, const TcParams &P)
 {
     const int len = P.bin_count + 1;
     float reg_w = 0.f, reg_h = 0.f, best_w = -1.f, best_h = -1.f;
     int idx_w = 0, idx_h = 0;
     int c0 = 0;
-    for (; c0 + 16 <= no; c0 += 16) ibin_chunk<16>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h);
+    for (; c0 + 16 <= no; c0 += 16) ibin_chunk<16>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h);
     const int rem = no - c0;
-    if (rem & 8) { ibin_chunk<8>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 8; }
-    if (rem & 4) { ibin_chunk<4>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 4; }
-    if (rem & 2) { ibin_chunk<2>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 2; }
-    if (rem & 1) { ibin_chunk<1>(taddr, c0, sb, srow, gx, gy, stride, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); }
+    if (rem & 8) { ibin_chunk<8>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 8; }
+    if (rem & 4) { ibin_chunk<4>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 4; }
+    if (rem & 2) { ibin_chunk<2>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 2; }
+    if (rem & 1) { ibin_chunk<1>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); }
 #pragma unroll
     for (int d = 0; d < 2; ++d) {
         float r = __fmul_rn(d == 0 ? reg_w : reg_h, 2.0f);
@@ -423,7 +423,7 @@ __device__ __forceinline__ void fused_epilogue(const TcParams &P, const TcLevel 
             if (score >= P.conf) {
                 const int ps = prow0 + my_src;
                 const float cx = decode_xy(sigmoidf_fast(t0), (float)(ps % L.nx), L.stride);
-                const float cy = decode_xy(sigmoidf_fast(t1), (float)(ps / L.nx), L.stride);
+                const float cy = decode_xy(sigmoidf_fast(t1), (float)(ps / L.nx), L.stride_y);
                 const float bw = decode_wh(sigmoidf_fast(t2), aw), bh = decode_wh(sigmoidf_fast(t3), ah);
                 float x1, y1, x2, y2;
                 xywh_to_corners(cx, cy, bw, bh, P.div_w, P.div_h, x1, y1, x2, y2);
@@ -445,7 +445,7 @@ __device__ __forceinline__ void fused_epilogue(const TcParams &P, const TcLevel 
         pass = pass && score >= P.conf;
         const float gx = (float)(p % L.nx), gy = (float)(p / L.nx);
         const float cx = decode_xy(sigmoidf_fast(tb[0]), gx, L.stride);
-        const float cy = decode_xy(sigmoidf_fast(tb[1]), gy, L.stride);
+        const float cy = decode_xy(sigmoidf_fast(tb[1]), gy, L.stride_y);
         const float bw = decode_wh(sigmoidf_fast(tb[2]), aw), bh = decode_wh(sigmoidf_fast(tb[3]), ah);
         float x1, y1, x2, y2;
         xywh_to_corners(cx, cy, bw, bh, P.div_w, P.div_h, x1, y1, x2, y2);

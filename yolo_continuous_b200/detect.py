@@ -142,6 +142,37 @@ def yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image
     return boxes
 
 
+def prepare_test_images(images, target_size, dtype=torch.float32, device="cuda:0"):
+    """Batched prepare_test_image (reference detect.py:16-26) for already decoded images (uint8 HWC, BGR as
+    cv2.imread returns them): letterbox + /255 + CHW on the device.  Returns (x [bs,3,H,W], original images)."""
+    from .image_enhance import letterbox_batch
+    x, _ = letterbox_batch(images, target_size, dtype, device)
+    return x, images
+
+
+def format_detections(rows, offsets, image_hw):
+    """The formatting loop of reference predict (detect.py:236-258) for a whole batch on the device.
+    rows [>=total,7] (y1,x1,y2,x2,obj,class_conf,class) and offsets [bs+1] as nms_device / PostBackbone return
+    them; image_hw int32 [bs,2] or [2] (shared).  Returns device tensors (box_xyxy int32 [cap,4], conf float32 [cap],
+    label int32 [cap]) valid up to offsets[bs]."""
+    _lib.require_cuda(rows, "rows")
+    dev = rows.device
+    bs = offsets.numel() - 1
+    hw = torch.as_tensor(image_hw, dtype=torch.int32).reshape(-1, 2).to(dev).contiguous()
+    if hw.shape[0] not in (1, bs):
+        raise _lib.YcError("format_detections: image_hw must hold one or bs (h, w) pairs")
+    cap = rows.shape[0]
+    box = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    conf = torch.empty((cap,), dtype=torch.float32, device=dev)
+    label = torch.empty((cap,), dtype=torch.int32, device=dev)
+    off = offsets.to(device=dev, dtype=torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.yc_format_detections(rows.contiguous().data_ptr(), off.data_ptr(), bs, hw.data_ptr(),
+                                                 2 if hw.shape[0] > 1 else 0, box.data_ptr(), conf.data_ptr(),
+                                                 label.data_ptr(), _lib.stream_ptr(dev)), "yc_format_detections")
+    return box, conf, label
+
+
 def detect_post_backbone(head, features, input_shape, image_shape, letterbox_image=True, conf_thres=0.3,
                          nms_thres=0.3):
     """The post-backbone half of reference detect.predict (detect.py:227-234) for an I*Detect head:
