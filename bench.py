@@ -150,7 +150,7 @@ def workload_config(bs, dtype):
 
 def pipelining_note(overlap):
     return ("two streams: the NMS kernels of step i run next to the head kernel of step i+1 (double-buffered workspaces); "
-            "all K steps complete inside the timed region") if overlap else "single stream"
+            "one CUDA graph launch per step; all K steps complete inside the timed region") if overlap else "single stream"
 
 
 def main():
@@ -186,7 +186,12 @@ def main():
     _lib.check(_lib.lib.yc_device_check(local), "yc_device_check")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the one collective of the path is a ~0.5 MB all-gather per step: one NCCL CTA, on the SM the head kernel
+        # leaves free for it (yc_reserve_sms), so that it runs next to the head kernel instead of displacing a CTA
+        if os.environ.get("YC_NCCL_CTAS", "") not in ("", "0"):
+            os.environ["NCCL_MAX_CTAS"] = os.environ["NCCL_MIN_CTAS"] = os.environ["YC_NCCL_CTAS"]
         dist.init_process_group("nccl", device_id=dev)
+        _lib.lib.yc_reserve_sms(int(os.environ.get("YC_RESERVE_SMS", "0")))
     W = max(args.warmup, 3)
     K = args.steps
     tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
@@ -194,8 +199,12 @@ def main():
     head = make_head().to(dev)
     pipe = PostBackbone(head, args.bs, SHAPES, tdt, INPUT_SHAPE, IMAGE_SHAPE, True, CONF, IOU, dev, use_graph=False,
                         fused=not args.unfused, double_buffer=world > 1, overlap=overlap)
-    GATHER_ROWS = 16384   # rows per rank in the fixed-size exchange (C2 produces ~2.7k per 64 images)
-    gather = DetectionGather(pipe.message(GATHER_ROWS).numel(), dev) if world > 1 else None
+    # rows per rank in the fixed-size exchange (C2 produces ~2.7k per 64 images; a rank with more says so in its
+    # header and the remainder is fetched with gather_detections): 115 KB, ~45 us with one NCCL CTA
+    GATHER_ROWS = int(os.environ.get("YC_GATHER_ROWS", "4096"))
+    # one collective per GATHER_EVERY steps (see DetectionGather): 8 steps = 512 images per rank per exchange
+    GATHER_EVERY = int(os.environ.get("YC_GATHER_EVERY", "8"))
+    gather = DetectionGather(pipe.message(GATHER_ROWS).numel(), dev, every=GATHER_EVERY) if world > 1 else None
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     xs = [torch.randn(args.bs, c, h, w, generator=g, device=dev).to(tdt) for c, (h, w) in zip(CH, SHAPES)]
     for d_, h_ in zip(xs, pipe.x_host):
@@ -207,11 +216,27 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
 
+    pipelined = overlap   # one CUDA graph per step: head of batch i next to the NMS kernels of batch i-1
+
     def step():
-        rows, _, counts, offsets = pipe.run_device(xs)
+        if pipelined:
+            prev = pipe.submit(xs)
+            if world > 1 and prev is not None:
+                gather.gather_async(pipe.message(GATHER_ROWS, previous=True))
+        else:
+            pipe.run_device(xs)
+            if world > 1:
+                gather.gather_async(pipe.message(GATHER_ROWS), stream=pipe.tail_stream)
+
+    def finish():
+        if pipelined:
+            pipe.drain()
+            if world > 1:
+                gather.gather_async(pipe.message(GATHER_ROWS))
         if world > 1:
-            gather.gather_async(pipe.message(GATHER_ROWS), stream=pipe.tail_stream)   # overlaps the next step
-        return rows, counts, offsets
+            gather.flush()
+            gather.wait()
+        pipe.wait()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -219,27 +244,42 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident throughput: K steps between two events, head kernel bracketed by its own events ----
+    # ---- device-resident throughput: K steps between two events (all work of the K steps completes inside) ----------
     for _ in range(W):
         step()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    finish()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
     sampler.start()
     sync_all()
     t0.record()
+    host_t0 = time.perf_counter()
     for i in range(K):
-        pipe.run_device(xs, head_events=ev[i])   # head kernel bracketed by events on its own stream
-        if world > 1:
-            gather.gather_async(pipe.message(GATHER_ROWS), stream=pipe.tail_stream)
-    if world > 1:
-        gather.wait()
-    pipe.wait()
+        step()
+    host_loop = time.perf_counter() - host_t0
+    finish()
     t1.record()
     sync_all()
+    ms = t0.elapsed_time(t1)
+    # ---- the same K steps issued call by call (two streams, no graph) with the head kernel and the NMS kernels
+    # bracketed by CUDA events on the streams they are launched on: per-kernel durations for the roofline ----------
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(K)]   # head start/end, NMS start/end
+    for _ in range(3):
+        pipe.run_device(xs)
+    pipe.wait()
+    sync_all()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for i in range(K):
+        pipe.run_device(xs, head_events=ev[i])
+    pipe.wait()
+    u1.record()
+    sync_all()
+    eager_ms = u0.elapsed_time(u1)
     clocks = sampler.stop()
     ms = t0.elapsed_time(t1)
-    head_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    head_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
+    tail_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in ev)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -249,7 +289,9 @@ def main():
     n_det = int(counts_host.sum())
 
     if args.profile:
-        print(json.dumps({"profile_run": True, "value": value, "ms_per_step": ms / K, "head_ms": head_ms}))
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "value": value, "ms_per_step": ms / K, "head_ms": head_ms, "nms_ms": tail_ms,
+                              "eager_ms_per_step": eager_ms / K, "host_enqueue_ms_per_step": host_loop / K * 1e3}))
         return
 
     # ---- end to end through the host-buffer call ------------------------------------------------------------
@@ -263,6 +305,7 @@ def main():
         if world > 1:
             gather.gather_async(pipe.message(GATHER_ROWS), stream=pipe.tail_stream)
     if world > 1:
+        gather.flush()
         gather.wait()
     torch.cuda.synchronize()
     e_ms = (time.perf_counter() - e0) * 1e3
@@ -329,7 +372,15 @@ def main():
     roofline = {"kernel": "head_tc_kernel" if args.dtype == "bf16" else "head_generic_kernel",
                 "stage": "S3 fused head->candidates (z never written)" if pipe.fused else "S1 head->z",
                 "peak_source": peak_src, "traffic": traffic, "kernel_ms": head_ms,
-                "kernel_share_of_step": head_ms / (ms / K), "bytes_per_launch": bytes_launch,
+                "kernel_share_of_step": head_ms / (ms / K),
+                "kernel_timing": f"CUDA events around each launch in a second pass of the same {K} steps issued call by call "
+                                 f"({eager_ms / K:.4f} ms per step; the graph-replayed timed region above cannot hold "
+                                 f"per-kernel events)",
+                # the three NMS kernels of a step, timed on their own stream (they run next to the NEXT step's head
+                # kernel when pipelined); head / (head + nms) is the share an ncu launch list (serialised) shows
+                "nms_kernels_ms": tail_ms,
+                "kernel_share_serialised": head_ms / (head_ms + tail_ms) if tail_ms else None,
+                "bytes_per_launch": bytes_launch,
                 "flops_per_launch": FLOPS_PER_IMG * args.bs}
     if pipe.fused:
         # S3 moves 5.73 MB/img but still needs 1.462 GFLOP/img: the tensor pipe binds first
@@ -343,7 +394,10 @@ def main():
         "metric": "post_backbone_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
-        "config": dict(workload_config(args.bs, args.dtype), pipelining=pipelining_note(overlap)),
+        "config": dict(workload_config(args.bs, args.dtype), pipelining=pipelining_note(overlap),
+                       **({"exchange": f"one NCCL all-gather per {GATHER_EVERY} steps: per rank and step the header + the first "
+                                       f"{GATHER_ROWS} detection rows; every step's detections reach every rank inside the "
+                                       f"timed region"} if world > 1 else {})),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
                 "d2h_bytes_per_step": pipe.d2h_bytes(total_rows), "ms_per_step": e_ms / K},

@@ -153,6 +153,10 @@ YC_API int yc_nms_from_candidates(const yc_nms_params *p, void *workspace, size_
  * batch in flight): yc_nms_workspace_reset clears the counters -- enqueue it behind yc_nms_from_candidates on the
  * NMS stream -- and yc_detect_fused_head_noreset is yc_detect_fused_head for a workspace that is already clear, so
  * that nothing but the head kernel runs on the head stream. */
+/* The persistent head kernels normally take every SM (one CTA each).  yc_reserve_sms(n) makes them leave n SMs free,
+ * e.g. one for the single-CTA NCCL all-gather of the previous batch's detections, which cannot share an SM with a
+ * head CTA and would otherwise delay the CTA it displaces by its whole duration.  Returns the previous value. */
+YC_API int yc_reserve_sms(int n);
 YC_API int yc_nms_workspace_reset(const yc_nms_params *p, void *workspace, size_t workspace_bytes, yc_stream_t stream);
 YC_API int yc_detect_fused_head_noreset(const yc_head_desc *desc, const yc_nms_params *p, void *workspace,
                                  size_t workspace_bytes, yc_stream_t stream);

@@ -575,6 +575,24 @@ def test_overlapped_pipeline_equals_serial():
     for w, g_ in zip(want, got):
         for a_, b_ in zip(w, g_):
             assert torch.equal(a_, b_)
+    # software-pipelined graph form: submit() returns the previous batch's results, drain() the last one's
+    got2 = []
+    for xs in batches:
+        r = over.submit(xs)
+        if r is not None:
+            tot = int(r[3][-1])
+            got2.append((r[0][:tot].clone(), r[1][:tot].clone(), r[2].clone(), r[3].clone()))
+    r = over.drain()
+    tot = int(r[3][-1])
+    got2.append((r[0][:tot].clone(), r[1][:tot].clone(), r[2].clone(), r[3].clone()))
+    for xs in batches[:3]:      # second round: graphs are replayed from the cache
+        r = over.submit(xs)
+    assert len(got2) == len(want)
+    for w, g_ in zip(want, got2):
+        for a_, b_ in zip(w, g_):
+            assert torch.equal(a_, b_)
+    r = over.drain()
+    assert torch.equal(r[0][:int(r[3][-1])], want[2][0])
     # host-buffer call through the overlapped pipeline
     for d_, s_ in zip(over.x_host, batches[0]):
         d_.copy_(s_)

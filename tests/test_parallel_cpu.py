@@ -89,6 +89,21 @@ def _worker_fixed(rank, world, port, q):
     for r, (c, total, rr) in enumerate(g.unpack(slot, bs, hdr_ints, cap)):
         ok &= c.tolist() == [1, 0, 2 + r] and int(total) == 3 + r
         ok &= rr[:int(total), 0].tolist() == [100.0 * r + i for i in range(3 + r)]
+    # grouped exchange: the messages of 3 consecutive steps travel in one collective; a 4th step is flushed alone
+    g3 = DetectionGather(msg.numel(), "cpu", every=3)
+    slots = []
+    for step in range(4):
+        rows[0, 1] = 10.0 * step + rank          # something that differs per step
+        slots.append(g3.gather_async(msg))
+    ok &= slots[:3] == [None, None, 0] and slots[3] is None
+    for r, steps in enumerate(g3.unpack(0, bs, hdr_ints, cap)):
+        ok &= len(steps) == 3
+        for k, (c, total, rr) in enumerate(steps):
+            ok &= c.tolist() == [1, 0, 2 + r] and int(total) == 3 + r and float(rr[0, 1]) == 10.0 * k + r
+    last = g3.flush()
+    ok &= last == 1
+    for r, steps in enumerate(g3.unpack(last, bs, hdr_ints, cap, n=1)):
+        ok &= float(steps[0][2][0, 1]) == 30.0 + r
     q.put((rank, ok))
     dist.destroy_process_group()
 

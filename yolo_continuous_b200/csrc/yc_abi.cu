@@ -178,6 +178,13 @@ static int fused_setup(const yc_head_desc *d, const yc_nms_params *p, void *work
     return YC_OK;
 }
 
+namespace yc { int set_reserved_sms(int n); }
+
+extern "C" int yc_reserve_sms(int n)
+{
+    return yc::set_reserved_sms(n);
+}
+
 extern "C" int yc_nms_workspace_reset(const yc_nms_params *p, void *workspace, size_t workspace_bytes, yc_stream_t stream_)
 {
     YC_REQUIRE(p && workspace, YC_ERR_INVALID, "yc_nms_workspace_reset: null argument");

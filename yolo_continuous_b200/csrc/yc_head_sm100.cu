@@ -271,6 +271,14 @@ static EncodeTiledFn encode_tiled()
 }
 
 static int g_num_sms = 0;
+static int g_reserved_sms = 0;   // yc_reserve_sms: SMs the persistent head kernels leave alone
+
+int set_reserved_sms(int n)
+{
+    const int old = g_reserved_sms;
+    g_reserved_sms = n < 0 ? 0 : n;
+    return old;
+}
 
 int launch_head_tc2(const TcMaps &maps, TcParams &P, int num_sms, cudaStream_t stream); // yc_head_sm100_2cta.cu
 
@@ -404,8 +412,9 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         YC_CUDA(cudaGetDevice(&dev));
         YC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    if (pair) return launch_head_tc2(maps, P, g_num_sms, stream);
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    if (pair) return launch_head_tc2(maps, P, g_num_sms - g_reserved_sms > 1 ? g_num_sms - g_reserved_sms : 2, stream);
+    const int sms = g_num_sms - g_reserved_sms > 0 ? g_num_sms - g_reserved_sms : 1;
+    const int grid = tiles < sms ? tiles : sms;
     const int threads = TC_NON_EPI_THREADS + 128 * na_tile;
     void (*kern)(const TcMaps, const TcParams) = P.debug ? (bk == 128 ? head_tc_kernel<128, true> : head_tc_kernel<64, true>)
                                                          : (bk == 128 ? head_tc_kernel<128, false> : head_tc_kernel<64, false>);
