@@ -97,12 +97,17 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
 
-    def start(self):
+    def start(self, wait_s=8.0):
+        """Starts nvidia-smi and waits for its first sample (it can take seconds to come up on an 8-GPU box)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < wait_s:
+                time.sleep(0.02)
+            self.skip = len(self.rows)   # samples taken before the timed region (idle clocks)
         except OSError:
             self.proc = None
 
@@ -115,6 +120,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        self.rows = self.rows[getattr(self, "skip", 0):] or self.rows
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -202,8 +208,9 @@ def main():
     # rows per rank in the fixed-size exchange (C2 produces ~2.7k per 64 images; a rank with more says so in its
     # header and the remainder is fetched with gather_detections): 115 KB, ~45 us with one NCCL CTA
     GATHER_ROWS = int(os.environ.get("YC_GATHER_ROWS", "4096"))
-    # one collective per GATHER_EVERY steps (see DetectionGather): 8 steps = 512 images per rank per exchange
-    GATHER_EVERY = int(os.environ.get("YC_GATHER_EVERY", "8"))
+    # one collective per GATHER_EVERY steps (see DetectionGather): 16 steps = 1024 images per rank per exchange
+    # (the host side of a NCCL call costs 0.2-0.6 ms at 2-8 ranks: one per step would make the loop host-bound)
+    GATHER_EVERY = int(os.environ.get("YC_GATHER_EVERY", "16"))
     gather = DetectionGather(pipe.message(GATHER_ROWS).numel(), dev, every=GATHER_EVERY) if world > 1 else None
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     xs = [torch.randn(args.bs, c, h, w, generator=g, device=dev).to(tdt) for c, (h, w) in zip(CH, SHAPES)]
@@ -250,7 +257,8 @@ def main():
     finish()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     sync_all()
     t0.record()
     host_t0 = time.perf_counter()
