@@ -42,7 +42,7 @@ __device__ __forceinline__ void ring_advance(int &s, uint32_t &parity, int n, in
 }
 
 template <bool DBG>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_NON_EPI_THREADS + 128 * 3, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(TC_MAX_REGS)
 head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -277,8 +277,10 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
 int launch_head_tc2(const TcMaps &maps, TcParams &P, int num_sms, cudaStream_t stream)
 {
     const size_t fixed = 1024 + (size_t)4 * P.na * P.slab_bytes + 512 + (size_t)T2_B_SLOTS * T2_B_BYTES;
+    // at most 214 KB: the rest of the SM's 228 KB stays free for the NMS kernels of the previous batch, which run next
+    // to this kernel on a second stream (largest of them: 17.5 KB + 1 KB reserved per CTA)
     int stages = T2_MAX_A_STAGES;
-    while (stages > 2 && fixed + (size_t)stages * T2_A_BYTES > 227 * 1024) --stages;
+    while (stages > 2 && fixed + (size_t)stages * T2_A_BYTES > 214 * 1024) --stages;
     const size_t smem_bytes = fixed + (size_t)stages * T2_A_BYTES;
     YC_REQUIRE(smem_bytes <= 227 * 1024, YC_ERR_UNSUPPORTED, "2-CTA head: needs %zu bytes of shared memory", smem_bytes);
     P.stages = stages;

@@ -266,18 +266,31 @@ __device__ __forceinline__ void grab_classes(uint32_t taddr, bool pass, float *_
                                              bool pair)
 {
     // at most 48 accumulators in registers at a time (the kernel is capped at TC_MAX_REGS registers)
+    // (as few, as wide loads as possible: the cost is per instruction)
     constexpr int H1 = NCH > 3 ? 3 : NCH, H2 = NCH - H1;
     uint32_t v[H1 * 16];
-#pragma unroll
-    for (int i = 0; i < H1; ++i) TmemLd<16>::ld(taddr + 5u + 16u * i, v + 16 * i);
+    if (H1 == 3) {
+        TmemLd<32>::ld(taddr + 5u, v);
+        TmemLd<16>::ld(taddr + 5u + 32u, v + 32);
+    } else if (H1 == 2) {
+        TmemLd<32>::ld(taddr + 5u, v);
+    } else {
+        TmemLd<16>::ld(taddr + 5u, v);
+    }
     tmem_ld_wait();
     if (H2 > 0) {
         if (pass) {
 #pragma unroll
             for (int j = 0; j < H1 * 16; ++j) qrow[j] = __uint_as_float(v[j]);
         }
-#pragma unroll
-        for (int i = 0; i < H2; ++i) TmemLd<16>::ld(taddr + 5u + 16u * (H1 + i), v + 16 * i);
+        if (H2 == 3) {
+            TmemLd<32>::ld(taddr + 5u + 16u * H1, v);
+            TmemLd<16>::ld(taddr + 5u + 16u * H1 + 32u, v + 32);
+        } else if (H2 == 2) {
+            TmemLd<32>::ld(taddr + 5u + 16u * H1, v);
+        } else {
+            TmemLd<16>::ld(taddr + 5u + 16u * H1, v);
+        }
         tmem_ld_wait();
     }
     tc_fence_before();
@@ -341,14 +354,14 @@ __device__ __forceinline__ void fused_epilogue(const TcParams &P, const TcLevel 
     const float aw = L.anchor_wh[2 * ar], ah = L.anchor_wh[2 * ar + 1];
     const float2 *sb = L.sb + ar * no;
     // box + objectness logits (columns 0..4), then the largest class logit
-    uint32_t v4[4], v1[1];
-    TmemLd<4>::ld(taddr, v4);
-    TmemLd<1>::ld(taddr + 4u, v1);
+    // one 8-column load (3 columns more than needed) instead of a 4- and a 1-column load: next to running MMAs a
+    // tcgen05.ld costs ~250 cycles per instruction, almost independent of its width
+    uint32_t v8[8];
+    TmemLd<8>::ld(taddr, v8);
     tmem_ld_wait();
     float tb[5];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) tb[j] = fmaf(__uint_as_float(v4[j]), sbv.v[j].x, sbv.v[j].y);
-    tb[4] = fmaf(__uint_as_float(v1[0]), sbv.v[4].x, sbv.v[4].y);
+    for (int j = 0; j < 5; ++j) tb[j] = fmaf(__uint_as_float(v8[j]), sbv.v[j].x, sbv.v[j].y);
     // Early reject on objectness alone: class scores are sigmoids (<= 1), so obj >= conf is necessary
     // for obj*cls >= conf.  At detection thresholds >99% of rows stop here after 5 columns; only
     // warps holding a survivor scan the class columns (exactly as the z path would see them).
