@@ -390,7 +390,9 @@ def main():
     except (OSError, ValueError):
         pass
     tflops = FLOPS_PER_IMG * args.bs / (head_ms / 1e3) / 1e12
-    roofline = {"kernel": "head_tc_kernel" if args.dtype == "bf16" else "head_generic_kernel",
+    kname = "head_generic_kernel" if args.dtype != "bf16" else \
+        ("head_tc2_kernel (CTA pairs, cta_group::2)" if pipe.fused and os.environ.get("YC_TC_2CTA", "1") != "0" else "head_tc_kernel")
+    roofline = {"kernel": kname,
                 "stage": "S3 fused head->candidates (z never written)" if pipe.fused else "S1 head->z",
                 "peak_source": peak_src, "traffic": traffic, "kernel_ms": head_ms,
                 "kernel_share_of_step": head_ms / (ms / K),

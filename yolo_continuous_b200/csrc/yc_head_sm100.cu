@@ -308,10 +308,10 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     // (K=128 x 2 stages measured 6 us slower on the C2 batch; YC_TC_BK overrides for experiments.)
     int bk = 64;
     { const char *e = getenv("YC_TC_BK"); if (e && (atoi(e) == 64 || atoi(e) == 128)) bk = atoi(e); }
-    // CTA pairs (cta_group::2) for the fused step: see yc_head_sm100_2cta.cu.  Experimental (measured 98 us against
-    // 86 us for the 1-CTA kernel on the C2 batch), so opt-in with YC_TC_2CTA=1.
-    bool pair = false;
-    { const char *e = getenv("YC_TC_2CTA"); if (e && atoi(e) == 1) pair = fused != nullptr && n_groups == 1 && npad % 16 == 0; }
+    // CTA pairs (cta_group::2) for the fused step: see yc_head_sm100_2cta.cu (measured 2-4 % faster than the 1-CTA
+    // kernel for batches of 32 images and more: 8 feature-map stages instead of 4).  YC_TC_2CTA=0 keeps the 1-CTA kernel.
+    bool pair = fused != nullptr && n_groups == 1 && npad % 16 == 0;
+    { const char *e = getenv("YC_TC_2CTA"); if (e && atoi(e) == 0) pair = false; }
     if (pair) bk = T2_BK; // feature-map box height of the CTA-pair kernel
     const int tile_px = pair ? 2 * TC_BM : TC_BM;
     const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * TC_B_BOX_BYTES;

@@ -5,8 +5,10 @@
 // (profiles/README.md).  In a pair, each CTA keeps its own 128 pixels of A and only HALF of the weight rows;
 // one cta_group::2 MMA (M = 256 pixels, N = 256) issued by the leader reads A and B from both CTAs and writes
 // each CTA's 128 x 256 fp32 accumulator into that CTA's TMEM.  Per CTA and MMA: 4 KB + 4 KB.
-// Half a weight k-block being 16 KB, eight weight slots hold all of W for K <= 512 (P3 and P4 of the COCO
-// head), so those levels stream only feature maps; the feature-map ring is separate and as deep as fits.
+// Half a weight k-block (64 k) being 16 KB, four weight slots hold all of W for K <= 256 (P3 of the COCO head, 3/4 of
+// the tiles), so that level streams only feature maps; deeper levels stream their weights through the same slots
+// from L2.  The feature-map ring is separate and as deep as fits (8 stages): the step is latency bound on feature-map
+// bytes in flight, and this is what the pair buys over the 1-CTA kernel (B 128 KB resident + 4 stages there).
 //
 // Roles per CTA: warp 0 feature-map producer (own A tile), warp 2 TMEM allocator then weight producer (own half of
 // the weight rows), bytes accounted on the LEADER's barriers; warps 1 and 3 MMA issuers (leader only, alternating
@@ -22,7 +24,9 @@ constexpr int T2_A_BYTES = TC_BM * T2_BK * 2;  // this CTA's 128 pixels x BK k (
 constexpr int T2_B_BOX = 128 * 64 * 2;         // 16 KB: this CTA's (up to) 128 weight rows x 64 k
 constexpr int T2_B_BYTES = (T2_BK / 64) * T2_B_BOX;
 #ifndef T2_B_SLOTS_K
-#define T2_B_SLOTS_K 512                       // weight slots cover K <= this (resident weights): 128 KB per CTA
+#define T2_B_SLOTS_K 256                       // weight slots cover K <= this (resident weights): 64 KB per CTA, which
+                                               // leaves 8 feature-map stages (128 KB in flight per CTA); with 512
+                                               // (P4 resident too, 4-5 stages) the kernel measured 4 % slower
 #endif
 constexpr int T2_B_SLOTS = T2_B_SLOTS_K / T2_BK;
 constexpr int T2_MAX_A_STAGES = 8;
