@@ -197,7 +197,8 @@ def main():
         if os.environ.get("YC_NCCL_CTAS", "") not in ("", "0"):
             os.environ["NCCL_MAX_CTAS"] = os.environ["NCCL_MIN_CTAS"] = os.environ["YC_NCCL_CTAS"]
         dist.init_process_group("nccl", device_id=dev)
-        _lib.lib.yc_reserve_sms(int(os.environ.get("YC_RESERVE_SMS", "0")))
+    if os.environ.get("YC_RESERVE_SMS"):
+        _lib.lib.yc_reserve_sms(int(os.environ["YC_RESERVE_SMS"]))
     W = max(args.warmup, 3)
     K = args.steps
     tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32

@@ -30,9 +30,16 @@ class IBin(HeadBase):
             for i in range(nl):
                 x[i] = raws[i]
             return x
-        z, raws = self._run(x[:nl], self.m, self.ia, self.im, _lib.YC_HEAD_IBIN, True, True,
+        # the exact-fp32 path decodes from the raw maps, so it always needs them; the tcgen05 path (bf16 maps whose
+        # levels meet the TMA alignment rules) decodes in its epilogue
+        import torch
+        tc = all(t.dtype == torch.bfloat16 and (t.shape[2] * t.shape[3]) % 8 == 0 and t.shape[1] % 8 == 0
+                 and t.data_ptr() % 16 == 0 for t in x[:nl])
+        want_raw = self.return_raw or not tc or self.head_path == _lib.YC_PATH_GENERIC
+        z, raws = self._run(x[:nl], self.m, self.ia, self.im, _lib.YC_HEAD_IBIN, True, want_raw,
                             no_out=self.nc + 5, bins=self.w_bin_sigmoid.bins, bin_count=self.bin_count)
         for i in range(nl):
             self._update_grid_cache(i, x[i].shape[2], x[i].shape[3], z.device)
-            x[i] = raws[i]
+            if self.return_raw:     # return_raw = False skips the 127-column raw maps (60 % of the output traffic)
+                x[i] = raws[i]
         return z, x
