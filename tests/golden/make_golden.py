@@ -233,6 +233,27 @@ def main():
         data = np.expand_dims(np.transpose((np.array(image_data, dtype='float32') / 255.), (2, 0, 1)), 0)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), image=img, target=np.asarray(target), data=data)
 
+    # --- 8f rank 4: RepConv.fuse_repvgg_block (nets/common.py:565-614) with and without the identity branch ---------
+    import copy
+    from nets.common import RepConv
+    for name, (c1, c2, s_) in (("repconv_identity", (8, 8, 1)), ("repconv_noid", (6, 10, 2))):
+        gen = torch.Generator().manual_seed(31)
+        rep = RepConv(c1, c2, 3, s_).eval()
+        for m_ in rep.modules():
+            if isinstance(m_, torch.nn.BatchNorm2d):
+                m_.running_mean.copy_(torch.randn(m_.running_mean.shape, generator=gen) * 0.3)
+                m_.running_var.copy_(torch.rand(m_.running_var.shape, generator=gen) + 0.5)
+                m_.weight.copy_(1.0 + 0.2 * torch.randn(m_.weight.shape, generator=gen))
+                m_.bias.copy_(0.1 * torch.randn(m_.bias.shape, generator=gen))
+        x = torch.randn(2, c1, 9, 7, generator=gen)
+        before = rep(x).numpy()
+        sd = sd_np(rep, "sd__")
+        fused = copy.deepcopy(rep)
+        fused.fuse_repvgg_block()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x.numpy(), before=before, after=fused(x).numpy(),
+                            weight=fused.rbr_reparam.weight.detach().numpy(), bias=fused.rbr_reparam.bias.detach().numpy(),
+                            c=np.asarray([c1, c2, s_]), **sd)
+
     # --- a9-a11: NMS ---------------------------------------------------------------------------
     nms_case("nms_clustered_lb", clustered_prediction(2, 320, 80, 7), 80, 0.25, 0.45, (640, 640), (512, 773), True)
     nms_case("nms_clustered_nolb", clustered_prediction(2, 320, 80, 8), 80, 0.3, 0.3, (640, 640), (480, 640), False)
