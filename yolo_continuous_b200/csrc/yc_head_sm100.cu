@@ -29,7 +29,10 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 {
     constexpr int TC_BK = BK;
     constexpr int TC_A_BYTES = TC_BM * BK * 2;
-    constexpr int TC_STAGE_BYTES = TC_A_BYTES + (BK / 64) * TC_B_BOX_BYTES;
+    // one weight box (64 k x Npad rows) takes P.b_slot_bytes of a stage: 32 KB for the 256-column tiles, 16 KB for IBin's
+    // one-anchor tiles, which buys those a deeper ring
+    const int TC_B_SLOT = (int)P.b_slot_bytes;
+    const int TC_STAGE_BYTES = TC_A_BYTES + (BK / 64) * TC_B_SLOT;
     extern __shared__ uint8_t smem_raw[];
     // carve: [stages: A|B] (1024-aligned) [slabs] [barriers]
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -116,7 +119,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         if (load_b) {
 #pragma unroll
                             for (int j = 0; j < BK / 64; ++j)
-                                tma_load_2d(sb + j * TC_B_BOX_BYTES, mb, &full_bar[stage], kb * TC_BK + j * 64, 0);
+                                tma_load_2d(sb + j * TC_B_SLOT, mb, &full_bar[stage], kb * TC_BK + j * 64, 0);
                         }
                     }
                 }
@@ -164,7 +167,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k)
                             mma_f16(tmem_d, da0 + so + (uint64_t)((k * 2048) >> 4),
-                                    db0 + so + (uint64_t)(((k / 4) * TC_B_BOX_BYTES + (k % 4) * 32) >> 4), idesc,
+                                    db0 + so + (uint64_t)(((k / 4) * TC_B_SLOT + (k % 4) * 32) >> 4), idesc,
                                     (uint32_t)((kb | k) != 0));
                     }
                     mma_commit(&empty_bar[stage]); // frees the smem slot when these MMAs retire
@@ -314,7 +317,8 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     { const char *e = getenv("YC_TC_2CTA"); if (e && atoi(e) == 0) pair = false; }
     if (pair) bk = T2_BK; // feature-map box height of the CTA-pair kernel
     const int tile_px = pair ? 2 * TC_BM : TC_BM;
-    const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * TC_B_BOX_BYTES;
+    const uint32_t b_slot_bytes = (uint32_t)round_up(npad * 64 * 2, 1024);   // npad is a multiple of 16: 2 KB steps
+    const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * b_slot_bytes;
     const size_t fixed = 1024 + (size_t)4 * na_tile * slab_bytes + 256;
     int stages = TC_MAX_STAGES;
     while (stages > 2 && fixed + (size_t)stages * stage_bytes > 227 * 1024) --stages;
@@ -357,6 +361,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     P.z = d->z;
     P.idesc = instr_desc_f16(/*bf16*/ 1, /*A MN-major*/ 1, /*B K-major*/ 0, (uint32_t)tile_px, (uint32_t)npad);
     P.b_box_bytes = (uint32_t)(pair ? npad / 2 : npad) * 64 * 2;
+    P.b_slot_bytes = b_slot_bytes;
     P.slab_bytes = slab_bytes;
     P.stages = stages;
     { const char *e = getenv("YC_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
@@ -376,6 +381,8 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         L.raw = lv.raw;
         L.K = lv.K; L.HW = HW; L.nx = lv.W;
         L.tiles_per_img = (HW + tile_px - 1) / tile_px;
+        L.boxes_per_img = (HW + 63) / 64;
+        L.n_boxes = d->bs * L.boxes_per_img;
         L.n_groups = n_groups;
         L.bmap0 = s * n_groups;
         L.tile_begin = tiles;
@@ -383,7 +390,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         L.stride = lv.stride;
         L.stride_y = lv.stride_y > 0.f ? lv.stride_y : lv.stride;
         for (int j = 0; j < YC_MAX_ANCHORS * 2; ++j) L.anchor_wh[j] = lv.anchor_wh[j];
-        tiles += d->bs * L.tiles_per_img * n_groups;
+        tiles += pair ? (L.n_boxes + 3) / 4 : d->bs * L.tiles_per_img * n_groups;
         {   // A: X [bs, K, HW] bf16, box {64 px, 64 k, 1}
             cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)lv.K, (cuuint64_t)d->bs};
             cuuint64_t gstr[2] = {(cuuint64_t)HW * 2, (cuuint64_t)HW * lv.K * 2};

@@ -110,9 +110,11 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
         int sa = 0;
         uint32_t pa = 0;
         for (int t = pair; t < P.total_tiles; t += n_pairs) {
-            const TileCoord tc = tile_coord_w(P, t, 2 * TC_BM);
+            const BoxTile tc = box_tile(P, t);
             const int nkb = (P.lv[tc.lv].K + T2_BK - 1) / T2_BK;
-            const int p_own = tc.p0 + TC_BM * (int)rank;
+            int b0, p0, b1, p1;   // this CTA's two 64-pixel boxes (possibly of different images)
+            box_coord(P.lv[tc.lv], P.bs, tc.j0 + 2 * (int)rank, b0, p0);
+            box_coord(P.lv[tc.lv], P.bs, tc.j0 + 2 * (int)rank + 1, b1, p1);
             const CUtensorMap *ma = &maps.a[tc.lv];
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&R.a_empty[sa], pa ^ 1u);
@@ -122,8 +124,8 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                         if (rank == 0) mbar_arrive(&R.a_full[sa]);
                     } else {
                         if (rank == 0) mbar_arrive_expect_tx(&R.a_full[sa], 2u * (uint32_t)T2_A_BYTES);
-                        tma_load_3d_pair(dst, ma, &R.a_full[sa], p_own, kb * T2_BK, tc.b);
-                        tma_load_3d_pair(dst + T2_A_BYTES / 2, ma, &R.a_full[sa], p_own + 64, kb * T2_BK, tc.b);
+                        tma_load_3d_pair(dst, ma, &R.a_full[sa], p0, kb * T2_BK, b0);
+                        tma_load_3d_pair(dst + T2_A_BYTES / 2, ma, &R.a_full[sa], p1, kb * T2_BK, b1);
                     }
                 }
                 __syncwarp();
@@ -135,14 +137,14 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
         int resident = -1;
         uint32_t pbits = 0; // bit s = parity of the next load into weight slot s
         for (int t = pair; t < P.total_tiles; t += n_pairs) {
-            const TileCoord tc = tile_coord_w(P, t, 2 * TC_BM);
+            const BoxTile tc = box_tile(P, t);
             const TcLevel &L = P.lv[tc.lv];
             const int nkb = (L.K + T2_BK - 1) / T2_BK;
-            const int wkey = tc.lv * YC_MAX_ANCHORS + tc.g;
+            const int wkey = tc.lv;   // the fused mode has one anchor group: the level identifies the weight tile
             const bool load_b = !(nkb <= T2_B_SLOTS && resident == wkey);
             resident = nkb <= T2_B_SLOTS ? wkey : -1;
             if (!load_b) continue;
-            const CUtensorMap *mb = &maps.b[L.bmap0 + tc.g];
+            const CUtensorMap *mb = &maps.b[L.bmap0];
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % T2_B_SLOTS;
                 mbar_wait(&R.b_empty[s], ((pbits >> s) & 1u) ^ 1u);
@@ -179,9 +181,9 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
             const uint32_t idesc = P.idesc;
             volatile int *turn = (volatile int *)(R.tmem_ptr + 1);
             for (int t = pair; t < P.total_tiles; t += n_pairs, ++it) {
-                const TileCoord tc = tile_coord_w(P, t, 2 * TC_BM);
+                const BoxTile tc = box_tile(P, t);
                 const int nkb = (P.lv[tc.lv].K + T2_BK - 1) / T2_BK;
-                const int wkey = tc.lv * YC_MAX_ANCHORS + tc.g;
+                const int wkey = tc.lv;
                 const bool load_b = !(nkb <= T2_B_SLOTS && resident == wkey);
                 resident = nkb <= T2_B_SLOTS ? wkey : -1;
                 const int buf = it & 1;
@@ -234,12 +236,14 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
         long long e_wait = 0, e_work = 0, e_max = 0;
         int e_slow = 0;
         for (int t = pair; t < P.total_tiles; t += n_pairs, ++it) {
-            const TileCoord tc = tile_coord_w(P, t, 2 * TC_BM);
+            const BoxTile tc = box_tile(P, t);
             const TcLevel &L = P.lv[tc.lv];
             const int buf = it & 1;
-            const int prow0 = tc.p0 + TC_BM * (int)rank + 32 * q;
-            const int nv = min(32, L.HW - prow0);
-            const int ar = tc.g * P.na + a;
+            int img, pbox;   // this warp's 32 rows are half of one 64-pixel box
+            box_coord(L, P.bs, tc.j0 + 2 * (int)rank + (q >> 1), img, pbox);
+            const int prow0 = pbox + 32 * (q & 1);
+            const int nv = img < P.bs ? min(32, L.HW - prow0) : 0;
+            const int ar = a;
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_MAX_N + a * P.no);
             if (tc.lv != cur_lv) { // fused mode: one anchor group per tile, so `ar` is fixed for this warp
                 sbv = load_box_sb(L.sb + ar * P.no, lane, P.nc);
@@ -256,7 +260,7 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                 if (lane == 0) mbar_arrive_leader(&R.tempty[buf]);
                 continue;
             }
-            fused_epilogue<true>(P, L, tc.b, prow0, nv, ar, taddr, slab, &R.tempty[buf], lane, sbv);
+            fused_epilogue<true>(P, L, img, prow0, nv, ar, taddr, slab, &R.tempty[buf], lane, sbv);
             if (eprof) {
                 const long long e2 = clock64();
                 e_wait += e1 - e0;

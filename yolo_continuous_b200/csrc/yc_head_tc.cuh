@@ -38,10 +38,13 @@ struct TcLevel {
     const float2 *sb;   // (scale, bias2) per column
     float *raw;         // [bs, na, HW, no] or null
     int n_groups;       // anchor groups per pixel tile: 1 (all anchors in one 256-column MMA tile) or na (IBin: one
-                        // 128-column MMA tile per anchor); tiles of a level are ordered pixel-block major, group minor
+                        // 128-column MMA tile per anchor); tiles of a level are ordered group major
     int bmap0;          // first weight tensor map of this level (one per group)
     int K, HW, nx;
     int tiles_per_img;  // ceil(HW / 128)
+    int boxes_per_img;  // ceil(HW / 64): 64-pixel TMA boxes per image (CTA-pair kernel: a tile is 4 consecutive boxes of the
+                        // level's box list, across image boundaries, so a 400-pixel P5 map wastes 12 % of a tile, not 28 %)
+    int n_boxes;        // bs * boxes_per_img
     int tile_begin;     // first tile id of this level in schedule order
     int row_off;        // first z row of this level
     float stride, stride_y;
@@ -63,6 +66,7 @@ struct TcParams {
     float *z;
     uint32_t idesc;
     uint32_t b_box_bytes;      // npad * 64 * 2: bytes one weight box brings
+    uint32_t b_slot_bytes;     // room one weight box takes in a stage of the 1-CTA kernel (b_box_bytes rounded up to 1 KB)
     uint32_t slab_bytes;       // per epilogue warp: 32*no*4 (z slab) or TC_QUEUE_ROWS*nc*4 (fused survivor queue)
     int debug;                 // YC_TC_DEBUG bits (timing experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA
     int stages;                // depth of the smem ring
@@ -91,13 +95,38 @@ __device__ __forceinline__ TileCoord tile_coord_w(const TcParams &P, int t, int 
     TileCoord c;
     c.lv = l;
     c.g = 0;
-    if (P.lv[l].n_groups > 1) { c.g = r % P.lv[l].n_groups; r /= P.lv[l].n_groups; }
+    if (P.lv[l].n_groups > 1) {   // group major: all pixel tiles of one anchor group are consecutive (weights stay put)
+        const int per_group = P.bs * P.lv[l].tiles_per_img;
+        c.g = r / per_group;
+        r -= c.g * per_group;
+    }
     c.b = r / P.lv[l].tiles_per_img;
     c.p0 = (r - c.b * P.lv[l].tiles_per_img) * width;
     return c;
 }
 
 __device__ __forceinline__ TileCoord tile_coord(const TcParams &P, int t) { return tile_coord_w(P, t, TC_BM); }
+
+// CTA-pair kernel: tile id -> (level, first 64-pixel box of the tile in the level's flat box list)
+struct BoxTile { int lv, j0; };
+__device__ __forceinline__ BoxTile box_tile(const TcParams &P, int t)
+{
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < YC_MAX_LEVELS; ++i)
+        if (i < P.n_lv && t >= P.lv[i].tile_begin) l = i;
+    BoxTile c;
+    c.lv = l;
+    c.j0 = (t - P.lv[l].tile_begin) * 4;
+    return c;
+}
+// box j of a level -> (image, first pixel); image = bs (out of range: TMA zero-fills, the epilogue skips) past the end
+__device__ __forceinline__ void box_coord(const TcLevel &L, int bs, int j, int &b, int &p0)
+{
+    if (j >= L.n_boxes) { b = bs; p0 = 0; return; }
+    b = j / L.boxes_per_img;
+    p0 = (j - b * L.boxes_per_img) * 64;
+}
 
 // Epilogue for W consecutive accumulator columns [c0, c0+W) of this thread's row.
 //   RAW:   slab[o] = t                     (pre-sigmoid map, forward()'s list `x`)
