@@ -39,8 +39,9 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     uint8_t *stage_base = smem;
     const int n_stages = P.stages;
     float *slabs = (float *)(smem + n_stages * TC_STAGE_BYTES);
-    const int n_epi_warps = 4 * P.na;
-    uint64_t *bars = (uint64_t *)((uint8_t *)slabs + (size_t)n_epi_warps * P.slab_bytes);
+    const int n_epi_warps = P.epi_warps;
+    const int n_slabs = P.ibin ? 4 : n_epi_warps;   // IBin: one slab per TMEM lane quadrant, shared by its three warps
+    uint64_t *bars = (uint64_t *)((uint8_t *)slabs + (size_t)n_slabs * P.slab_bytes);
     uint64_t *full_bar = bars;                        // [TC_MAX_STAGES]
     uint64_t *empty_bar = bars + TC_MAX_STAGES;       // [TC_MAX_STAGES]
     uint64_t *tfull_bar = bars + 2 * TC_MAX_STAGES;   // [2]
@@ -185,7 +186,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // ===================== epilogue: TMEM -> sigmoid/decode -> slab -> bulk store =====================
         const int e = warp - TC_NON_EPI_THREADS / 32;
         const int q = warp & 3;     // TMEM lane quadrant this warp may read
-        const int a = e >> 2;       // anchor handled by this warp
+        const int a = P.ibin ? 0 : e >> 2;       // anchor of the tile handled by this warp (IBin: one anchor per tile)
         float *slab = (float *)((uint8_t *)slabs + (size_t)e * P.slab_bytes);
         const int no = P.no, no_out = P.no_out;
         int it = 0, cur_lv = -1;
@@ -224,6 +225,45 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane, sbv);
                 continue;
             }
+            if (P.ibin) {
+                // IBin (nets/ibin.py:56-72): 127 accumulator columns and as many sigmoids per row made this epilogue the
+                // bottleneck with one warp per quadrant (1.28 ms against 0.30 ms with the epilogue switched off), so
+                // the three warps of a quadrant split the columns [x y | w bins | h bins] [obj + half of the classes]
+                // [rest] and fill ONE slab per quadrant, which the first of them stores.
+                const int part = e >> 2;
+                const int len = P.bin_count + 1, s1 = 2 + 2 * len;       // s1: objectness column
+                const int sc = s1 + (no - s1) / 3;                       // classes are shared 1/3 : 2/3 by parts 1 and 2
+                float *zs = (float *)((uint8_t *)slabs + (size_t)q * P.slab_bytes), *rs = zs + 32 * no_out;
+                if (part == 0) {
+                    if (lane == 0) bulk_wait_read0();   // the previous stores from this quadrant's slab have been read out
+                    __syncwarp();
+                }
+                named_bar_sync(1 + q, 96);
+                // part 0: [x y | w block]   part 1: [h block] + objectness and a third of the classes   part 2: the rest
+                const int cb = part == 0 ? 0 : (part == 1 ? 2 + len : sc), ce = part == 0 ? 2 + len : (part == 1 ? sc : no);
+                if (L.raw) epi_range_raw(taddr, cb, ce, sb, rs + lane * no);
+                if (P.write_z) {
+                    float *zrow = zs + lane * no_out;
+                    if (part == 0) epi_range_ibin(taddr, 0, 2 + len, true, false, sb, zrow, gx, gy, L.stride, L.stride_y, aw, ah, P);
+                    if (part == 1) {
+                        epi_range_ibin(taddr, 2 + len, s1, false, true, sb, zrow, gx, gy, L.stride, L.stride_y, aw, ah, P);
+                        epi_range_sig(taddr, s1, sc, sb, zrow, 2 * len - 2);
+                    }
+                    if (part == 2) epi_range_sig(taddr, sc, no, sb, zrow, 2 * len - 2);
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                named_bar_sync(5 + q, 96);              // all three parts of the rows are in the slab
+                if (part == 0 && nv > 0) {
+                    if (L.raw) slab_store(L.raw + (((size_t)tc.b * P.na_real + ar) * L.HW + prow0) * no, rs, nv, no, lane);
+                    if (P.write_z)
+                        slab_store(P.z + ((size_t)tc.b * P.rows_total + L.row_off + (size_t)ar * L.HW + prow0) * no_out, zs, nv,
+                                   no_out, lane);
+                }
+                continue;
+            }
             if (L.raw) {
                 if (lane == 0) bulk_wait_read0(); // previous store from this slab has been read out
                 __syncwarp();
@@ -234,8 +274,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (P.write_z) {
                 if (lane == 0) bulk_wait_read0();
                 __syncwarp();
-                if (P.ibin) epi_row_ibin(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, L.stride_y, aw, ah, P);
-                else epi_row<false>(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, L.stride_y, aw, ah);
+                epi_row<false>(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, L.stride_y, aw, ah);
             }
             // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA warp
             tc_fence_before();
@@ -305,8 +344,13 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
 
     // per epilogue warp: z slab (32 rows) or, in the fused mode, the survivor queue (TC_QUEUE_ROWS x nc floats)
     const int no_out = ibin ? d->no - 2 * (d->bin_count + 1) + 2 : d->no;
+    // IBin: one slab per quadrant holding the z rows and (if asked for) the raw rows of 32 pixels
+    bool any_raw = false;
+    for (int i = 0; i < d->nl; ++i) any_raw = any_raw || d->level[i].raw != nullptr;
     const uint32_t slab_bytes = fused ? (uint32_t)round_up(TC_QUEUE_ROWS * (d->no - 5) * 4, 16)
-                                      : (uint32_t)round_up(32 * d->no * 4, 16);
+                                : ibin ? (uint32_t)round_up(32 * no_out * 4 + (any_raw ? 32 * d->no * 4 : 0), 16)
+                                       : (uint32_t)round_up(32 * d->no * 4, 16);
+    const int epi_warps = ibin ? 12 : 4 * na_tile;
     // K=64 per stage: 4 stages in the fused mode (no z slabs in shared memory), 2 next to the slabs.
     // (K=128 x 2 stages measured 6 us slower on the C2 batch; YC_TC_BK overrides for experiments.)
     int bk = 64;
@@ -319,7 +363,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     const int tile_px = pair ? 2 * TC_BM : TC_BM;
     const uint32_t b_slot_bytes = (uint32_t)round_up(npad * 64 * 2, 1024);   // npad is a multiple of 16: 2 KB steps
     const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * b_slot_bytes;
-    const size_t fixed = 1024 + (size_t)4 * na_tile * slab_bytes + 256;
+    const size_t fixed = 1024 + (size_t)(ibin ? 4 : 4 * na_tile) * slab_bytes + 256;
     int stages = TC_MAX_STAGES;
     while (stages > 2 && fixed + (size_t)stages * stage_bytes > 227 * 1024) --stages;
     const size_t smem_bytes = fixed + (size_t)stages * stage_bytes;
@@ -350,6 +394,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     memset(&P, 0, sizeof(P));
     P.n_lv = n;
     P.bs = d->bs; P.na = na_tile; P.no = d->no; P.npad = npad;
+    P.epi_warps = epi_warps;
     P.na_real = d->na; P.no_out = no_out;
     P.rows_total = rows_total;
     P.write_z = d->kind != YC_HEAD_RAW ? 1 : 0;
@@ -422,7 +467,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     if (pair) return launch_head_tc2(maps, P, g_num_sms - g_reserved_sms > 1 ? g_num_sms - g_reserved_sms : 2, stream);
     const int sms = g_num_sms - g_reserved_sms > 0 ? g_num_sms - g_reserved_sms : 1;
     const int grid = tiles < sms ? tiles : sms;
-    const int threads = TC_NON_EPI_THREADS + 128 * na_tile;
+    const int threads = TC_NON_EPI_THREADS + 32 * epi_warps;
     void (*kern)(const TcMaps, const TcParams) = P.debug ? (bk == 128 ? head_tc_kernel<128, true> : head_tc_kernel<64, true>)
                                                          : (bk == 128 ? head_tc_kernel<128, false> : head_tc_kernel<64, false>);
     YC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

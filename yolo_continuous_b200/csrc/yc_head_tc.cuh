@@ -55,7 +55,9 @@ struct TcParams {
     TcLevel lv[YC_MAX_LEVELS]; // in schedule order (largest K first)
     int n_lv;
     int total_tiles;
-    int bs, na, no, npad;      // na = anchors per MMA tile (epilogue warp groups), no = accumulator columns per anchor
+    int bs, na, no, npad;      // na = anchors per MMA tile, no = accumulator columns per anchor
+    int epi_warps;             // epilogue warps: 4 per anchor of the tile; IBin (one anchor per tile, 127 sigmoids per row):
+                               // 12 = 3 per TMEM lane quadrant, each taking a third of the columns
     int na_real;               // anchors of the head (raw map indexing)
     int no_out;                // columns of a z row (no; IBin: nc + 5)
     int ibin, bin_count;       // IBin decode (nets/ibin.py:56-72)
@@ -205,21 +207,51 @@ __device__ __forceinline__ void ibin_chunk(uint32_t taddr, int c0, const float2 
     }
 }
 
-__device__ __forceinline__ void epi_row_ibin(uint32_t taddr, int no, const float2 *__restrict__ sb, float *__restrict__ srow,
-                                             float gx, float gy, float stride, float stride_y, float aw, float ah, const TcParams &P)
+// sigmoid of the accumulator columns [cb, ce) (objectness / classes) into srow[o - shift]: no per-column case analysis
+template <int W>
+__device__ __forceinline__ void sig_chunk(uint32_t taddr, int c0, const float2 *__restrict__ sb, float *__restrict__ srow, int shift)
+{
+    uint32_t v[W];
+    TmemLd<W>::ld(taddr + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const float2 s_b = __ldg(sb + c0 + j);
+        srow[c0 + j - shift] = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
+    }
+}
+__device__ __forceinline__ void epi_range_sig(uint32_t taddr, int cb, int ce, const float2 *__restrict__ sb, float *__restrict__ srow,
+                                              int shift)
+{
+    int c0 = cb;
+    for (; c0 + 32 <= ce; c0 += 32) sig_chunk<32>(taddr, c0, sb, srow, shift);
+    const int rem = ce - c0;
+    if (rem & 16) { sig_chunk<16>(taddr, c0, sb, srow, shift); c0 += 16; }
+    if (rem & 8) { sig_chunk<8>(taddr, c0, sb, srow, shift); c0 += 8; }
+    if (rem & 4) { sig_chunk<4>(taddr, c0, sb, srow, shift); c0 += 4; }
+    if (rem & 2) { sig_chunk<2>(taddr, c0, sb, srow, shift); c0 += 2; }
+    if (rem & 1) { sig_chunk<1>(taddr, c0, sb, srow, shift); }
+}
+
+// columns [cb, ce) of the IBin row's box part; final_w / final_h: this range held all of the w / h block, finish it
+__device__ __forceinline__ void epi_range_ibin(uint32_t taddr, int cb, int ce, bool final_w, bool final_h, const float2 *__restrict__ sb,
+                                               float *__restrict__ srow, float gx, float gy, float stride, float stride_y,
+                                               float aw, float ah, const TcParams &P)
 {
     const int len = P.bin_count + 1;
     float reg_w = 0.f, reg_h = 0.f, best_w = -1.f, best_h = -1.f;
     int idx_w = 0, idx_h = 0;
-    int c0 = 0;
-    for (; c0 + 16 <= no; c0 += 16) ibin_chunk<16>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h);
-    const int rem = no - c0;
+    int c0 = cb;
+    for (; c0 + 32 <= ce; c0 += 32) ibin_chunk<32>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h);
+    const int rem = ce - c0;
+    if (rem & 16) { ibin_chunk<16>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 16; }
     if (rem & 8) { ibin_chunk<8>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 8; }
     if (rem & 4) { ibin_chunk<4>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 4; }
     if (rem & 2) { ibin_chunk<2>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 2; }
     if (rem & 1) { ibin_chunk<1>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); }
 #pragma unroll
     for (int d = 0; d < 2; ++d) {
+        if (!(d == 0 ? final_w : final_h)) continue;
         float r = __fmul_rn(d == 0 ? reg_w : reg_h, 2.0f);
         r = __fadd_rn(r, -1.0f);
         r = __fmul_rn(r, P.bin_step);
@@ -227,6 +259,19 @@ __device__ __forceinline__ void epi_row_ibin(uint32_t taddr, int no, const float
         res = fminf(fmaxf(res, 0.0f), 4.0f);
         srow[2 + d] = __fmul_rn(res, d == 0 ? aw : ah);
     }
+}
+
+// raw columns [cb, ce) of this thread's row into the slab row
+__device__ __forceinline__ void epi_range_raw(uint32_t taddr, int cb, int ce, const float2 *__restrict__ sb, float *__restrict__ srow)
+{
+    int c0 = cb;
+    for (; c0 + 32 <= ce; c0 += 32) epi_chunk<32, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+    const int rem = ce - c0;
+    if (rem & 16) { epi_chunk<16, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 16; }
+    if (rem & 8) { epi_chunk<8, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 8; }
+    if (rem & 4) { epi_chunk<4, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 4; }
+    if (rem & 2) { epi_chunk<2, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 2; }
+    if (rem & 1) { epi_chunk<1, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); }
 }
 
 
