@@ -317,15 +317,28 @@ def main():
         return
 
     # ---- end to end through the host-buffer call ------------------------------------------------------------
+    # every step: H2D of that step's feature maps from pinned host memory, the kernels, D2H of its detections; with the
+    # pipelined call the H2D of step i+1 runs under the kernels and the read-back of step i
+    def host_step():
+        if overlap:
+            return pipe.submit_host()
+        out_ = pipe.run_host()
+        return out_
+
     for _ in range(3):
-        pipe.run_host()
+        host_step()
+    if overlap:
+        pipe.drain_host()
     sync_all()
     e0 = time.perf_counter()
-    total_rows = 0
+    total_rows, out = 0, None
     for _ in range(K):
-        out = pipe.run_host()
+        o = host_step()
+        out = o if o is not None else out
         if world > 1:
             gather.gather_async(pipe.message(GATHER_ROWS), stream=pipe.tail_stream)
+    if overlap:
+        out = pipe.drain_host()
     if world > 1:
         gather.flush()
         gather.wait()

@@ -593,6 +593,17 @@ def test_overlapped_pipeline_equals_serial():
             assert torch.equal(a_, b_)
     r = over.drain()
     assert torch.equal(r[0][:int(r[3][-1])], want[2][0])
+    # pipelined host-buffer calls: H2D of batch i+1 under the kernels / read-back of batch i
+    hosts = [[t.cpu().pin_memory() for t in xs] for xs in batches]
+    outs = [over.submit_host(h) for h in hosts] + [over.drain_host()]
+    assert outs[0] is None
+    for w, out in zip(want, outs[1:]):
+        off = w[3].cpu().numpy()
+        for b in range(bs):
+            ref = w[0][off[b]:off[b + 1]].cpu().numpy()
+            assert (out[b] is None) == (len(ref) == 0)
+            if out[b] is not None:
+                assert np.array_equal(out[b], ref)
     # host-buffer call through the overlapped pipeline
     for d_, s_ in zip(over.x_host, batches[0]):
         d_.copy_(s_)

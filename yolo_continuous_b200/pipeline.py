@@ -98,6 +98,7 @@ class PostBackbone:
         self._pgraphs = {}
         self._in_flight = False
         self._eager_dirty = False
+        self._hp = None
         self.use_graph = use_graph and not self.overlap
         if self.overlap:
             with torch.cuda.device(dev):
@@ -324,6 +325,63 @@ class PostBackbone:
                 self.rows_host[spec:total].copy_(rows[spec:total], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
         host = self.rows_host.numpy()
+        return [None if off[b + 1] == off[b] else host[off[b]:off[b + 1]].copy() for b in range(self.bs)]
+
+    # ---- host path, software pipelined: H2D of batch i+1 under the kernels and the D2H of batch i -----------------
+    def submit_host(self, features_host=None):
+        """Pipelined run_host for a stream of batches (needs overlap=True): the pinned host maps of THIS batch are
+        copied on a copy stream into the second set of device buffers while the kernels and the result read-back of
+        the previous batch are still in flight, so the PCIe link never idles between batches.  Returns the previous
+        batch's detections (reference result type, list of None | ndarray[n,7]) or None on the first call;
+        drain_host() returns the last batch's."""
+        if not self.overlap:
+            raise _lib.YcError("submit_host() needs overlap=True")
+        src = self.x_host if features_host is None else features_host
+        with torch.cuda.device(self.device):
+            if self._hp is None:
+                dev = self.device
+                self._hp = {
+                    "x": [self.x_dev, [torch.empty_like(t) for t in self.x_dev]],
+                    "copy": torch.cuda.Stream(device=dev),
+                    "h2d": [torch.cuda.Event(), torch.cuda.Event()], "xfree": [torch.cuda.Event(), torch.cuda.Event()],
+                    "d2h": [torch.cuda.Event(), torch.cuda.Event()],
+                    "meta": [self.meta_host, torch.empty_like(self.meta_host).pin_memory()],
+                    "rows": [self.rows_host[:self.spec_rows], torch.empty((self.spec_rows, 7), dtype=torch.float32).pin_memory()],
+                    "k": 0, "pending": None}
+            hp = self._hp
+            k = hp["k"] = hp["k"] ^ 1
+            main = torch.cuda.current_stream()
+            with torch.cuda.stream(hp["copy"]):
+                hp["copy"].wait_event(hp["xfree"][k])           # the head kernel that last read this set is done
+                for d_, h_ in zip(hp["x"][k], src):
+                    d_.copy_(h_, non_blocking=True)
+                hp["h2d"][k].record(hp["copy"])
+            main.wait_event(hp["h2d"][k])
+            rows, _, _, _ = self.run_device(hp["x"][k])          # head on `main`, NMS kernels on the tail stream
+            hp["xfree"][k].record(main)
+            c = self.cur
+            with torch.cuda.stream(self.tail_stream):            # read-back in order behind the NMS kernels
+                hp["meta"][k].copy_(self.metas[c], non_blocking=True)
+                hp["rows"][k].copy_(rows[:self.spec_rows], non_blocking=True)
+                hp["d2h"][k].record(self.tail_stream)
+            prev, hp["pending"] = hp["pending"], (k, c)
+        return None if prev is None else self._collect_host(*prev)
+
+    def drain_host(self):
+        if self._hp is None or self._hp["pending"] is None:
+            return None
+        prev, self._hp["pending"] = self._hp["pending"], None
+        return self._collect_host(*prev)
+
+    def _collect_host(self, k, c):
+        hp = self._hp
+        hp["d2h"][k].synchronize()
+        off = hp["meta"][k][self.bs:].numpy()
+        total = int(off[-1])
+        host = hp["rows"][k].numpy()
+        if total > self.spec_rows:   # rare: more detections than the speculative read-back holds
+            extra = self.rows_bufs[c][:total].cpu().numpy()
+            return [None if off[b + 1] == off[b] else extra[off[b]:off[b + 1]].copy() for b in range(self.bs)]
         return [None if off[b + 1] == off[b] else host[off[b]:off[b + 1]].copy() for b in range(self.bs)]
 
     def h2d_bytes(self):
