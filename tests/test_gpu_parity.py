@@ -403,6 +403,25 @@ def test_tcgen05_head_vs_oracle_bf16(kind):
         assert torch.equal(tr[i], raws[i])
 
 
+def test_fp32_maps_bf16_switch_matches_bf16_inputs():
+    """head.fp32_maps = "bf16": float32 maps are cast and take the tcgen05 kernel -- same result as passing bf16 maps."""
+    from yolo_continuous_b200.nets import IDetect
+    g = torch.Generator().manual_seed(4)
+    head = IDetect(80, [[12, 16, 19, 36, 40, 28], [36, 75, 76, 55, 72, 146], [142, 110, 192, 243, 459, 401]], (64, 128, 256))
+    head = head.to(DEV).eval()
+    head.stride = torch.tensor([8.0, 16.0, 32.0])
+    head.return_raw = False
+    xs = [torch.randn(2, c, h, w, generator=g).to(DEV) for c, (h, w) in zip((64, 128, 256), [(16, 16), (8, 8), (4, 4)])]
+    z_exact = head(list(xs))[0]
+    z_bf = head([x.to(torch.bfloat16) for x in xs])[0]
+    head.fp32_maps = "bf16"
+    z_sw = head(list(xs))[0]
+    assert torch.equal(z_sw, z_bf) and not torch.equal(z_sw, z_exact)
+    head.fp32_maps = "nope"
+    with pytest.raises(ValueError):
+        head(list(xs))
+
+
 def test_tcgen05_head_tiny_nc1():
     """nc=1 (config C1 shape: N = 18 -> one 32-column MMA), even row length (6 floats)."""
     from yolo_continuous_b200 import _lib

@@ -23,6 +23,10 @@ class HeadBase(nn.Module):
     export = False  # nets/idetect.py:9
     head_path = _lib.YC_PATH_AUTO   # which kernel family runs the conv (see include/yc_b200.h)
     return_raw = True               # eval forward returns (z, raw list) as the reference does
+    # float32 feature maps run the exact FFMA kernel (1e-5 parity, ~18 TFLOP/s).  "bf16" casts them to bfloat16 first
+    # and takes the tcgen05 kernel (1e-3 parity, the precision class of the TF32 convolutions torch uses on a GPU by
+    # default, ~15x faster end to end); bfloat16 maps always take the tcgen05 kernel.
+    fp32_maps = "exact"
 
     def _init_common(self, nc, anchors, no):
         self.nc = nc
@@ -76,6 +80,10 @@ class HeadBase(nn.Module):
     # ---- one C-ABI call for all levels --------------------------------------------------------
     def _run(self, xs, convs, ias, ims, kind, want_z, want_raw, no_out=None, bins=None, bin_count=0):
         nl = len(xs)
+        if self.fp32_maps == "bf16" and not (torch.is_grad_enabled() and any(t.requires_grad for t in xs)):
+            xs = [t.to(torch.bfloat16) if isinstance(t, torch.Tensor) and t.dtype == torch.float32 else t for t in xs]
+        elif self.fp32_maps not in ("exact", "bf16"):
+            raise ValueError(f"fp32_maps must be 'exact' or 'bf16', got {self.fp32_maps!r}")
         x0 = xs[0]
         for t in xs:
             if not isinstance(t, torch.Tensor) or t.dim() != 4:
