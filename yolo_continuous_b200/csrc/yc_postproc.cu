@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int
         if (lane == 0) {
             s_total = running;
             if (flat) s_koff[nc] = running;
-            atomicExch(&ws.img_total[b], running + 1); // publish
+            if (blockIdx.y == 0) atomicExch(&ws.img_total[b], running + 1); // publish
         }
     }
     // chained scan: sum of the totals of images 0..b-1
@@ -438,13 +438,15 @@ __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int
         int base = 0;
         for (int w = 0; w < FINISH_NT / 32; ++w) base += s_red[w];
         s_base = base;
-        out_counts[b] = s_total;
-        out_offsets[b] = base;
-        if (b == bs - 1) out_offsets[bs] = base + s_total;
+        if (blockIdx.y == 0) {
+            out_counts[b] = s_total;
+            out_offsets[b] = base;
+            if (b == bs - 1) out_offsets[bs] = base + s_total;
+        }
     }
     __syncthreads(); // also makes warp 0's kept_off writes visible to the block
     const int img_base = s_base;
-    if (s_total == 0) return;
+    if (s_total == 0 || (int)blockIdx.y * FINISH_NT >= s_total) return;
 
     double off[2] = {0, 0}, scl[2] = {1, 1}, ims[2] = {1, 1};
     if (cp.enabled) {
@@ -494,8 +496,10 @@ __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int
         o[4] = oc.x; o[5] = oc.y; o[6] = (float)c;
         out_idx[oidx] = row;
     };
+    // gridDim.y CTAs share the rows of an image (one per image at detection thresholds; several when most of the
+    // 25 200 rows of a low-threshold image survive): slice y takes the k with (k / FINISH_NT) % gridDim.y == y
     if (flat) {
-        for (int k = tid; k < total; k += FINISH_NT) {
+        for (int k = blockIdx.y * FINISH_NT + tid; k < total; k += FINISH_NT * gridDim.y) {
             int lo = 0, hi = nc; // last c with s_koff[c] <= k (empty classes share their successor's offset)
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int
             write_row(lo, ws.kept_row[ib + s_soff[lo] + (k - s_koff[lo])], (size_t)img_base + k);
         }
     } else {
-        for (int c = wid; c < nc; c += FINISH_NT / 32) {
+        for (int c = wid + blockIdx.y * (FINISH_NT / 32); c < nc; c += (FINISH_NT / 32) * gridDim.y) {
             const int nk = ws.kept_count[sb + c];
             if (nk == 0) continue;
             const int *kept_row = ws.kept_row + ib + ws.seg_off[sb + c];
@@ -547,7 +551,13 @@ int launch_nms_tail(const yc_nms_params *p, const NmsWs &ws, float *out_rows, in
     nms_segment_kernel<<<dim3((p->nc + spc - 1) / spc, p->bs), NMS_NT, 0, stream>>>(p->rows, p->nc,
                                                                                      thr_to_f32_floor(p->nms_thres), spc, ws);
     CorrectParams cp{p->correct_boxes, p->letterbox, p->input_h, p->input_w, (const int *)p->image_hw, p->image_hw_stride};
-    finish_kernel<<<p->bs, FINISH_NT, 0, stream>>>(p->bs, p->rows, p->nc, ws, out_counts, out_offsets, out_rows, out_idx, cp);
+    // slices per image: enough CTAs to cover the GPU when the batch alone does not (the chained scan over images needs
+    // the y == 0 CTAs of all earlier images to be scheduled first: x is the fastest grid dimension, so they are)
+    int slices = 1;
+    if (p->bs < 32)
+        while (slices < 16 && (long long)p->bs * slices < 148 && (long long)slices * FINISH_NT * 4 < p->rows) slices *= 2;
+    finish_kernel<<<dim3(p->bs, slices), FINISH_NT, 0, stream>>>(p->bs, p->rows, p->nc, ws, out_counts, out_offsets, out_rows,
+                                                               out_idx, cp);
     YC_CUDA(cudaGetLastError());
     return YC_OK;
 }
