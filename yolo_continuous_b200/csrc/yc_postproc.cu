@@ -158,6 +158,9 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, const flo
     const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+    // disjoint boxes (the vast majority of pairs): the quotient is +-0 or NaN, never above a non-negative threshold --
+    // skip the two areas and the IEEE division
+    if ((w == 0.0f || h == 0.0f) && thr_f >= 0.0f) return false;
     const float inter = __fmul_rn(w, h);
     const float aa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
     const float ab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
