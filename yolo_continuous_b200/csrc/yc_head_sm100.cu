@@ -81,9 +81,6 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // descriptors formed by one 64-bit add).
     const bool skip_epi = DBG && (P.debug & 1), skip_mma = DBG && (P.debug & 2), skip_tma = DBG && (P.debug & 4);
     const bool prof = DBG && (P.debug & 8) && blockIdx.x == 0;
-    // polling experiments (DBG only): 16 = one epilogue thread polls tfull, the others wait at a named barrier;
-    // 32 / 64 = only lane 0 of the producer / MMA warp polls
-    const bool epi_one = DBG && (P.debug & 16), prod_one = DBG && (P.debug & 32), mma_one = DBG && (P.debug & 64);
     if (warp == 0) {
         // ===================== TMA producer =====================
         int stage = 0;
@@ -105,8 +102,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint32_t tx = (uint32_t)TC_A_BYTES + (load_b ? (BK / 64) * P.b_box_bytes : 0u);
             for (int kb = 0; kb < nkb; ++kb) {
                 const long long w0 = prof ? clock64() : 0;
-                if (prod_one) { if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1u); __syncwarp(); }
-                else mbar_wait(&empty_bar[stage], phase ^ 1u);
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
                 const long long w1 = prof ? clock64() : 0;
                 if (prof) p_wait += w1 - w0;
                 if (elect_one()) {
@@ -157,8 +153,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_MAX_N;
             for (int kb = 0; kb < nkb; ++kb) {
                 w0 = prof ? clock64() : 0;
-                if (mma_one) { if (lane == 0) mbar_wait(&full_bar[stage], phase); __syncwarp(); }
-                else mbar_wait(&full_bar[stage], phase);
+                mbar_wait(&full_bar[stage], phase);
                 const long long w1 = prof ? clock64() : 0;
                 if (prof) { m_wf += w1 - w0; ++m_kb; }
                 tc_fence_after();
@@ -208,12 +203,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 sbv = load_box_sb(sb, lane, P.nc);
                 cur_lv = tc.lv;
             }
-            if (epi_one) {
-                if (e == 0) { if (lane == 0) mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u); __syncwarp(); }
-                named_bar_sync(1, 32 * n_epi_warps);
-            } else {
-                mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
-            }
+            mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             if (skip_epi) {
                 tc_fence_before();

@@ -104,7 +104,6 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
     // weight slots keeps its W resident, so only the first of consecutive tiles with the same weight tile loads it).
     // All role loops are whole-warp loops with one elected issuing lane (see yc_head_sm100.cu for why).
     const bool skip_epi = DBG && (P.debug & 1), skip_mma = DBG && (P.debug & 2), skip_tma = DBG && (P.debug & 4);
-    const bool spin_epi = DBG && (P.debug & 16), spin_mma = DBG && (P.debug & 32);   // polling experiments
     if (warp == 0) {
         // ===================== feature-map (A) producer, both CTAs =====================
         int sa = 0;
@@ -190,14 +189,12 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_MAX_N;
                 // both CTAs' epilogues drained the buffer (also orders this warp's tfull arrival after the previous
                 // phase of tfull[buf], which the epilogues waited for)
-                if (spin_mma) mbar_spin(&R.tempty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-                else mbar_wait(&R.tempty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                mbar_wait(&R.tempty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
                     const int s = kb % T2_B_SLOTS;
                     if ((g & 1) == me) {
                         if (load_b) mbar_wait(&R.b_full[s], (pbits >> s) & 1u);
-                        if (spin_mma) mbar_spin(&R.a_full[sa], pa);
-                        else mbar_wait(&R.a_full[sa], pa);
+                        mbar_wait(&R.a_full[sa], pa);
                         tc_fence_after();
                         const uint64_t da = da0 + (uint64_t)((uint32_t)(sa * T2_A_BYTES) >> 4);
                         const uint64_t db = db0 + (uint64_t)((uint32_t)(s * T2_B_BYTES) >> 4);
@@ -250,8 +247,7 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                 cur_lv = tc.lv;
             }
             const long long e0 = eprof ? clock64() : 0;
-            if (spin_epi) mbar_spin(&R.tfull[buf], (uint32_t)(it >> 1) & 1u);
-            else mbar_wait(&R.tfull[buf], (uint32_t)(it >> 1) & 1u);
+            mbar_wait(&R.tfull[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             const long long e1 = eprof ? clock64() : 0;
             if (skip_epi) {

@@ -74,18 +74,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// busy poll (no hardware suspend between polls)
-__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity)
-{
-    while (!mbar_test(bar, parity)) {
-    }
-}
-template <bool SPIN> __device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity)
-{
-    if (SPIN) mbar_spin(bar, parity);
-    else mbar_wait(bar, parity);
-}
-
 // ---- TMA -------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m)
 {
