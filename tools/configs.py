@@ -66,3 +66,50 @@ for name, cls, ch in (("c5_iaux_1280_bf16", IAuxDetect, bench.CH * 2), ("c5_ibin
     out[name] = {"bs": bs, "rows_per_image": rows, "forward_ms": ms, "images_per_s": bs / ms * 1e3,
                  "tflops": flops / ms / 1e9, "hbm_gbs_algorithmic": bytes_ / ms / 1e6}
 print(json.dumps(out, indent=1))
+
+# ---- C1: yolov7-tiny head (nc = 1, ch 128/256/512), one 640x640 image, conf / iou 0.3 (detect.py:271-272) ---------
+import time
+import numpy as np
+from yolo_continuous_b200 import detect as b200
+from yolo_continuous_b200.nets import IDetect
+from oracle import ref_port
+TINY_ANCHORS = [[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]]
+ch1 = (128, 256, 512)
+g1 = torch.Generator().manual_seed(0)
+h1 = IDetect(1, TINY_ANCHORS, ch1).eval()
+with torch.no_grad():
+    for n_, p_ in h1.named_parameters():
+        if n_.endswith("weight"):
+            p_.copy_(0.02 * torch.randn(p_.shape, generator=g1))
+        elif n_.startswith("im."):
+            p_.copy_(1.0 + 0.02 * torch.randn(p_.shape, generator=g1))
+        elif n_.endswith("bias"):
+            p_.copy_(torch.full(p_.shape, -2.0))
+h1.stride = torch.tensor(bench.STRIDES)
+xs_cpu = [torch.randn(1, c, h, w, generator=g1) for c, (h, w) in zip(ch1, bench.SHAPES)]
+params = {"anchors": h1.anchor_grid.detach().reshape(3, -1, 2).numpy(), "w": [m.weight.detach()[:, :, 0, 0] for m in h1.m],
+          "b": [m.bias.detach() for m in h1.m], "ia": [a.implicit.detach().reshape(-1) for a in h1.ia],
+          "im": [m.implicit.detach().reshape(-1) for m in h1.im]}
+ts = []
+with torch.no_grad():
+    for i in range(7):
+        t0 = time.perf_counter()
+        ref = ref_port.post_backbone(params, [x.clone() for x in xs_cpu], bench.STRIDES, 1, (640, 640), (512, 773), True, 0.3, 0.3)
+        ts.append(time.perf_counter() - t0)
+cpu_ms = statistics.median(ts[2:]) * 1e3
+h1 = h1.to(dev)
+out_c1 = {}
+for dt in (torch.float32, torch.bfloat16):
+    xs1 = [x.to(dev).to(dt) for x in xs_cpu]
+    lat = []
+    with torch.no_grad():
+        for i in range(30):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = b200.detect_post_backbone(h1, list(xs1), (640, 640), (512, 773), True, 0.3, 0.3)
+            lat.append(time.perf_counter() - t0)
+    out_c1[str(dt)] = {"post_backbone_ms_p50_host_clock": statistics.median(lat[5:]) * 1e3,
+                       "detections": 0 if res[0] is None else len(res[0])}
+out_c1["reference_cpu_port_ms"] = cpu_ms
+out_c1["reference_cpu_detections"] = 0 if ref[0] is None else len(ref[0])
+print(json.dumps({"c1_tiny_bs1": out_c1}, indent=1))

@@ -219,7 +219,7 @@ class PostBackbone:
                     self._launch(features)          # warm-up outside capture (lazy module/attribute setup)
                     torch.cuda.current_stream().synchronize()
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
                         self._launch(features)
                     if len(self._graphs) > 8:
                         self._graphs.clear()
@@ -257,7 +257,7 @@ class PostBackbone:
                 torch.cuda.current_stream().wait_event(self.ev_tail[1])
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
                     self._pipelined_step(features, c)
                 if len(self._pgraphs) > 16:
                     self._pgraphs.clear()
