@@ -90,48 +90,65 @@ struct GenericLevel {
     float anchor_wh[YC_MAX_ANCHORS * 2];
 };
 
-constexpr int GM = 64, GN = 64, GK = 16;
+constexpr int GM = 128, GN = 64, GK = 16;
 
-// grid: (ceil(HW/64), ceil(N/64), bs)   block: 256 threads, 4x4 outputs each
+// grid: (ceil(HW/128), ceil(N/64), bs)   block: 256 threads, 8 pixels x 4 channels each.
+// Exact binary32: every output is one fmaf chain over k in ascending order (what the oracle computes), whatever the
+// tiling.  Operands come out of shared memory as float4 (32 FMAs per 3 loads) and the next k-tile is fetched from global
+// memory into registers while the current one is multiplied.
 template <typename XT, typename WT>
 __global__ void __launch_bounds__(256) head_generic_kernel(GenericLevel L, int na, int no, int rows_total, int decode)
 {
-    __shared__ float As[GK][GM + 4];
-    __shared__ float Bs[GK][GN + 4];
+    __shared__ __align__(16) float As[GK][GM];
+    __shared__ __align__(16) float Bs[GK][GN + 4];   // +4: the transposing stores below hit 8 banks instead of 1
     const int N = na * no;
     const int p0 = blockIdx.x * GM, c0 = blockIdx.y * GN, b = blockIdx.z;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4; // tx -> pixels, ty -> channels
+    // tx -> pixels tx*4..+3 and 64+tx*4..+3 (two conflict-free float4 reads), ty -> channels ty*4..+3
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const XT *x = (const XT *)L.x + (size_t)b * L.K * L.HW;
     const WT *w = (const WT *)L.w;
-    float acc[4][4];
+    float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+    float ra[8], rb[4];   // the next k-tile's global loads: A 16 x 128 (coalesced along pixels), B 64 x 16 (along k)
+#define YC_GENERIC_FETCH(K0)                                                                          \
+    {                                                                                                 \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                               \
+            const int e = tid + i * 256, kk = e >> 7, pp = e & 127;                                   \
+            const int k = (K0) + kk, p = p0 + pp;                                                     \
+            ra[i] = (k < L.K && p < L.HW) ? to_f32<XT>(x[(size_t)k * L.HW + p]) : 0.f;                \
+        }                                                                                             \
+        _Pragma("unroll") for (int i = 0; i < 4; ++i) {                                               \
+            const int e = tid + i * 256, cc = e >> 4, kk = e & 15;                                    \
+            const int k = (K0) + kk, c = c0 + cc;                                                     \
+            rb[i] = (k < L.K && c < N) ? to_f32<WT>(w[(size_t)c * L.K + k]) : 0.f;                    \
+        }                                                                                             \
+    }
+    YC_GENERIC_FETCH(0)
     for (int k0 = 0; k0 < L.K; k0 += GK) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { // A: 16 x 64, coalesced along pixels
-            const int e = tid + i * 256, kk = e >> 6, pp = e & 63;
-            const int k = k0 + kk, p = p0 + pp;
-            As[kk][pp] = (k < L.K && p < L.HW) ? to_f32<XT>(x[(size_t)k * L.HW + p]) : 0.f;
+        for (int i = 0; i < 8; ++i) {
+            const int e = tid + i * 256;
+            As[e >> 7][e & 127] = ra[i];
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { // B: 64 x 16, contiguous along k
-            const int e = tid + i * 256, cc = e >> 4, kk = e & 15;
-            const int k = k0 + kk, c = c0 + cc;
-            Bs[kk][cc] = (k < L.K && c < N) ? to_f32<WT>(w[(size_t)c * L.K + k]) : 0.f;
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            Bs[e & 15][e >> 4] = rb[i];
         }
         __syncthreads();
+        if (k0 + GK < L.K) YC_GENERIC_FETCH(k0 + GK)
 #pragma unroll
         for (int kk = 0; kk < GK; ++kk) {
-            float a[4], bb[4];
+            const float4 a0 = *(const float4 *)&As[kk][tx * 4], a1 = *(const float4 *)&As[kk][64 + tx * 4];
+            const float4 b4 = *(const float4 *)&Bs[kk][ty * 4];
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][ty * 4 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
         }
@@ -144,8 +161,8 @@ __global__ void __launch_bounds__(256) head_generic_kernel(GenericLevel L, int n
         const int a = c / no, o = c - a * no;
         const float sc = L.scale[c], bi = L.bias2[c];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int p = p0 + tx * 4 + i;
+        for (int i = 0; i < 8; ++i) {
+            const int p = p0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + i - 4);
             if (p >= L.HW) continue;
             const float t = fmaf(acc[i][j], sc, bi);
             if (L.raw) L.raw[(((size_t)b * na + a) * L.HW + p) * no + o] = t;
@@ -158,6 +175,7 @@ __global__ void __launch_bounds__(256) head_generic_kernel(GenericLevel L, int n
             }
         }
     }
+#undef YC_GENERIC_FETCH
 }
 
 // ------------------------------------------------------------------------------------------------
