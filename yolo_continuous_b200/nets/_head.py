@@ -23,9 +23,9 @@ class HeadBase(nn.Module):
     export = False  # nets/idetect.py:9
     head_path = _lib.YC_PATH_AUTO   # which kernel family runs the conv (see include/yc_b200.h)
     return_raw = True               # eval forward returns (z, raw list) as the reference does
-    # float32 feature maps run the exact FFMA kernel (1e-5 parity, ~18 TFLOP/s).  "bf16" casts them to bfloat16 first
+    # float32 feature maps run the exact FFMA kernel (1e-5 parity, ~27 TFLOP/s).  "bf16" casts them to bfloat16 first
     # and takes the tcgen05 kernel (1e-3 parity, the precision class of the TF32 convolutions torch uses on a GPU by
-    # default, ~15x faster end to end); bfloat16 maps always take the tcgen05 kernel.
+    # default, ~10x faster end to end); bfloat16 maps always take the tcgen05 kernel.
     fp32_maps = "exact"
 
     def _init_common(self, nc, anchors, no):
