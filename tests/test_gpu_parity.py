@@ -684,6 +684,39 @@ def test_fused_step_full_size_weight_resident():
         assert torch.equal(a_, b_)
 
 
+def test_c5_c3_full_sizes_fused_equals_two_call_path():
+    """The largest shapes of BASELINE.json: 1280x1280 (100 800 rows per image, C5) with a batch whose rows do not
+    divide into tiles evenly, at the mAP-eval thresholds of C3 (conf 0.001 / iou 0.65: hundreds of thousands of
+    candidates) -- the fused step (CTA-pair kernel, cross-image tiles) against head + NMS, bit for bit, plus the
+    size-independent properties of the result (sorted per class, counts/offsets consistent, rows from valid indices)."""
+    from yolo_continuous_b200.pipeline import PostBackbone
+    ch, shapes, bs = (256, 512, 1024), [(160, 160), (80, 80), (40, 40)], 3
+    head = _bench_like_head(80, ch, 21).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(22)
+    xs = [torch.randn(bs, c, h, w, generator=g, device=DEV).to(torch.bfloat16) for c, (h, w) in zip(ch, shapes)]
+    res = []
+    for fused in (True, False):
+        pipe = PostBackbone(head, bs, shapes, torch.bfloat16, (1280, 1280), (720, 1280), True, 0.001, 0.65, DEV,
+                            use_graph=False, fused=fused)
+        rows, idx, counts, offsets = pipe.run_device(xs)
+        assert pipe.fused == fused and pipe.rows == 100800
+        tot = int(offsets[-1])
+        res.append((rows[:tot].clone(), idx[:tot].clone(), counts.clone(), offsets.clone()))
+        del pipe
+    for a_, b_ in zip(res[0], res[1]):
+        assert torch.equal(a_, b_)
+    rows, idx, counts, offsets = res[0]
+    assert int(counts.sum()) == rows.shape[0] > 50000
+    assert torch.equal(offsets[1:] - offsets[:-1], counts) and int(idx.min()) >= 0 and int(idx.max()) < 100800
+    for b in range(bs):
+        r = rows[int(offsets[b]):int(offsets[b + 1])]
+        cls, score = r[:, 6], r[:, 4] * r[:, 5]
+        assert bool((cls[1:] >= cls[:-1]).all())                                   # classes ascending
+        same = cls[1:] == cls[:-1]
+        assert bool((score[1:][same] <= score[:-1][same]).all())                   # scores descending within a class
+        assert bool((score >= 0.001).all())
+
+
 def test_tcgen05_ibin_full_width_vs_generic_kernel():
     """IBin (N = 3 x 127) at 1280-class feature-map sizes, bs 2: tensor-core path (one 128-column MMA tile per
     anchor) against the exact-FFMA path on the same bf16 inputs."""
