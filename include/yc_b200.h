@@ -157,6 +157,9 @@ YC_API int yc_nms_from_candidates(const yc_nms_params *p, void *workspace, size_
  * e.g. one for the single-CTA NCCL all-gather of the previous batch's detections, which cannot share an SM with a
  * head CTA and would otherwise delay the CTA it displaces by its whole duration.  Returns the previous value. */
 YC_API int yc_reserve_sms(int n);
+/* Device-to-device copy on `stream` (the per-step staging of a rank's detection message: one driver call instead of a
+ * framework tensor copy on the host's critical path). */
+YC_API int yc_copy_async(void *dst, const void *src, size_t bytes, yc_stream_t stream);
 YC_API int yc_nms_workspace_reset(const yc_nms_params *p, void *workspace, size_t workspace_bytes, yc_stream_t stream);
 YC_API int yc_detect_fused_head_noreset(const yc_head_desc *desc, const yc_nms_params *p, void *workspace,
                                  size_t workspace_bytes, yc_stream_t stream);

@@ -41,7 +41,7 @@ EXPORTS = ["yc_last_error", "yc_version", "yc_device_check", "yc_head_pack_bytes
            "yc_head_forward", "yc_decode_box", "yc_nms_workspace_bytes", "yc_nms_batched",
            "yc_nms_single", "yc_box_iou", "yc_cvt_bbox", "yc_detect_fused",
            "yc_detect_fused_head", "yc_nms_from_candidates", "yc_nms_workspace_reset", "yc_detect_fused_head_noreset",
-           "yc_letterbox_batch", "yc_format_detections", "yc_reserve_sms"]
+           "yc_letterbox_batch", "yc_format_detections", "yc_reserve_sms", "yc_copy_async"]
 
 
 def _load():
@@ -72,6 +72,7 @@ def _load():
     lib.yc_nms_from_candidates.argtypes = [C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_reserve_sms.argtypes = [C.c_int]
+    lib.yc_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.yc_letterbox_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.yc_format_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]

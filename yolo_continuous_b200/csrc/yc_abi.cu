@@ -180,6 +180,13 @@ static int fused_setup(const yc_head_desc *d, const yc_nms_params *p, void *work
 
 namespace yc { int set_reserved_sms(int n); }
 
+extern "C" int yc_copy_async(void *dst, const void *src, size_t bytes, yc_stream_t stream)
+{
+    YC_REQUIRE(dst && src, YC_ERR_INVALID, "yc_copy_async: null argument");
+    YC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return YC_OK;
+}
+
 extern "C" int yc_reserve_sms(int n)
 {
     return yc::set_reserved_sms(n);
