@@ -1,5 +1,5 @@
 """all_gather_into_tensor latency on this box for the message sizes of the detection exchange (tools only)."""
-import os, sys, torch, torch.distributed as dist
+import os, torch, torch.distributed as dist
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -69,7 +69,7 @@ print(json.dumps(out, indent=1))
 
 # ---- C1: yolov7-tiny head (nc = 1, ch 128/256/512), one 640x640 image, conf / iou 0.3 (detect.py:271-272) ---------
 import time
-import numpy as np
+
 from yolo_continuous_b200 import detect as b200
 from yolo_continuous_b200.nets import IDetect
 from oracle import ref_port
