@@ -113,3 +113,19 @@ def test_yolo_correct_boxes_host_matches_oracle():
         xy, wh = (rows[:, 0:2] + rows[:, 2:4]) / 2, rows[:, 2:4] - rows[:, 0:2]
         got = detect.yolo_correct_boxes(xy, wh, (640, 640), np.array(shp), lb).astype(np.float32)
         assert np.array_equal(got, want)
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure: nothing under the package may import it (or the reference checkout), and the
+    package has no CPU implementation to fall back to (CPU tensors raise, see test_product_refuses_cpu_tensors)."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bad = []
+    for f in glob.glob(os.path.join(root, "yolo_continuous_b200", "**", "*.py"), recursive=True):
+        src = open(f).read()
+        if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "/root/reference" in src:
+            bad.append(f)
+    assert not bad, bad
+    for f in glob.glob(os.path.join(root, "yolo_continuous_b200", "csrc", "*.cu*")):
+        assert "oracle" not in open(f).read().lower().replace("oracle computes", ""), f
