@@ -165,3 +165,27 @@ def test_repconv_reparam_vs_reference(name):
         fuse_repvgg_block(rep)
         assert rep.deploy and rep.rbr_dense is None and rep.rbr_1x1 is None and rep.rbr_identity is None
         assert np.array_equal(rep(x).numpy(), fx["after"])
+
+
+def test_oracle_nms_matches_torchvision_on_random_boxes():
+    """torchvision.ops.nms is the third-party routine behind detect.py:133; where the wheel is installed (it is in
+    the build image) the C restatement is checked against it directly on seeded random boxes with exact ties,
+    duplicates and degenerate boxes, at thresholds that are and are not representable in binary32."""
+    tv = pytest.importorskip("torchvision")
+    import torch
+    rng = np.random.default_rng(17)
+    for n, thr in ((1, 0.5), (7, 0.3), (64, 0.45), (257, 0.65), (500, 0.5), (300, 1.0 / 3.0), (120, 0.0)):
+        xy = rng.uniform(0, 100, (n, 2)).astype(np.float32)
+        wh = rng.uniform(0, 40, (n, 2)).astype(np.float32)
+        boxes = np.concatenate([xy, xy + wh], 1)
+        scores = rng.uniform(0, 1, n).astype(np.float32)
+        if n > 10:
+            boxes[5] = boxes[3]                      # duplicate box
+            scores[5] = scores[3]                    # ... with a tied score (stable order decides)
+            boxes[7, 2:] = boxes[7, :2]              # zero-area box
+            scores[8] = scores[9]                    # tie between different boxes
+            boxes[11] = np.round(boxes[11])          # integer coordinates: IoU exactly representable more often
+            boxes[12] = boxes[11] + np.float32([0, 0, 10, 0])
+        want = tv.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr).numpy()
+        got = orc.nms(boxes, scores, thr)
+        assert np.array_equal(got, want), (n, thr)
