@@ -254,6 +254,29 @@ def main():
                             weight=fused.rbr_reparam.weight.detach().numpy(), bias=fused.rbr_reparam.bias.detach().numpy(),
                             c=np.asarray([c1, c2, s_]), **sd)
 
+    # --- 8f rank 1: the formatting loop of predict (detect.py:236-258).  It lives inside predict(), which cannot run
+    # (Windows checkpoint path, cv2.imshow), so the reference's own source lines of that block are executed here on
+    # synthetic NMS results, with stand-ins for the names the block reads. ---------------------------------------
+    import inspect
+    import textwrap
+    import types
+    src = inspect.getsource(ref_detect.predict)
+    block = textwrap.dedent(src[src.index("    if results[0] is not None:"):src.index("        show_bbox(original_image, target_boxes)")])
+    rng = np.random.default_rng(41)
+    n, (ih, iw) = 40, (480, 640)
+    rows = np.concatenate([rng.uniform(-30, 700, (n, 4)), rng.uniform(0, 1, (n, 2)), rng.integers(0, 80, (n, 1))], 1).astype(np.float32)
+    rows[0, :4] = [-0.5, -0.0, 479.999, 640.0]          # edge values of floor / clamp
+    rows[1, :4] = [3.0, 5.0, 480.0, 639.5]
+    ns = {"np": np, "results": [rows.copy()], "original_image": np.zeros((ih, iw, 3), np.uint8),
+          "plan": types.SimpleNamespace(labels=[str(i) for i in range(80)]), "colors": [(0, 0, 0)] * 80,
+          "TargetBox": ref_detect.TargetBox, "print": lambda *a, **k: None}
+    exec(block, ns)
+    tb = ns["target_boxes"]
+    np.savez_compressed(os.path.join(HERE, "format_predict.npz"), rows=rows, image_hw=np.asarray([ih, iw]),
+                        box=np.asarray([[t.left, t.top, t.right, t.bottom] for t in tb], dtype=np.int64),
+                        conf=np.asarray([t.score for t in tb], dtype=np.float32),
+                        label=np.asarray([int(t.label) for t in tb], dtype=np.int64))
+
     # --- a9-a11: NMS ---------------------------------------------------------------------------
     nms_case("nms_clustered_lb", clustered_prediction(2, 320, 80, 7), 80, 0.25, 0.45, (640, 640), (512, 773), True)
     nms_case("nms_clustered_nolb", clustered_prediction(2, 320, 80, 8), 80, 0.3, 0.3, (640, 640), (480, 640), False)

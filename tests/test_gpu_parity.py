@@ -543,6 +543,18 @@ def test_letterbox_batch_mixed_sizes_vs_oracle():
         assert np.array_equal(x[i:i + 1].cpu().numpy(), orc.prepare_test_image(img, (640, 640))), f"image {i}"
 
 
+def test_format_detections_vs_golden():
+    """Device formatting against the output of the reference's own formatting lines (detect.py:236-258)."""
+    from yolo_continuous_b200 import detect
+    fx = load("format_predict")
+    n = fx["rows"].shape[0]
+    box, conf, label = detect.format_detections(torch.from_numpy(fx["rows"]).to(DEV), torch.tensor([0, n], dtype=torch.int32),
+                                                fx["image_hw"].astype(np.int32))
+    assert np.array_equal(box[:n].cpu().numpy(), fx["box"])
+    assert np.array_equal(conf[:n].cpu().numpy(), fx["conf"])
+    assert np.array_equal(label[:n].cpu().numpy(), fx["label"])
+
+
 def test_format_detections_vs_oracle():
     """Formatting loop of predict (detect.py:236-258) on the device for a batch with an empty image."""
     from yolo_continuous_b200 import detect

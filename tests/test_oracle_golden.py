@@ -121,6 +121,13 @@ def test_oracle_prepare_test_image_bit_exact(name):
     assert np.array_equal(got, fx["data"])
 
 
+def test_oracle_format_detections_vs_reference_block():
+    """The reference's own formatting lines (detect.py:236-258, executed on synthetic rows by make_golden.py)."""
+    fx = load("format_predict")
+    box, conf, label = orc.format_detections(fx["rows"], tuple(int(v) for v in fx["image_hw"]))
+    assert np.array_equal(box, fx["box"]) and np.array_equal(conf, fx["conf"]) and np.array_equal(label, fx["label"])
+
+
 def test_oracle_format_detections():
     """Formatting loop of predict (detect.py:236-258): floor, clamp, obj*cls_conf, int label."""
     rows = np.array([[-3.7, 10.2, 50.9, 700.5, 0.9, 0.5, 3.0],
