@@ -221,21 +221,9 @@ __global__ void __launch_bounds__(256) ibin_decode_kernel(const float *__restric
 }
 
 // Variant A decode (reference detect.py:29-87): conv NCHW -> normalised rows.
-__global__ void __launch_bounds__(256) decode_box_kernel(const float *__restrict__ conv, int bs, int na, int no, int ny,
-                                                         int nx, float aw0, float ah0, float aw1, float ah1, float aw2,
-                                                         float ah2, float aw3, float ah3, float *__restrict__ out)
+__device__ __forceinline__ float decode_box_value(float t, int j, int p, int a, int ny, int nx, const float *aw)
 {
-    const int HW = ny * nx;
-    const size_t total = (size_t)bs * na * HW * no;
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= total) return;
-    const int j = (int)(i % no);
-    const size_t r = i / no;
-    const int p = (int)(r % HW);
-    const size_t ba = r / HW; // b*na + a
-    const int a = (int)(ba % na);
-    float s = sigmoidf_fast(conv[(ba * no + j) * HW + p]);
-    const float aw[8] = {aw0, ah0, aw1, ah1, aw2, ah2, aw3, ah3};
+    float s = sigmoidf_fast(t);
     if (j < 2) {
         float v = __fmul_rn(s, 2.0f);
         v = __fadd_rn(v, -0.5f);
@@ -247,7 +235,34 @@ __global__ void __launch_bounds__(256) decode_box_kernel(const float *__restrict
         v = __fmul_rn(v, aw[a * 2 + (j - 2)]);
         s = __fdiv_rn(v, j == 2 ? (float)nx : (float)ny);
     }
-    out[i] = s;
+    return s;
+}
+
+struct Anchors8 { float v[8]; };
+
+// The map is channel-major ([no][HW] per anchor), the rows are channel-minor ([HW][no]): a CTA transposes a
+// [no][TP pixels] tile through shared memory, so that both the reads (along pixels) and the writes (TP consecutive rows
+// = one contiguous span of the output) are coalesced.  grid (ceil(HW/TP), bs*na).
+template <int TP>
+__global__ void __launch_bounds__(256) decode_box_kernel(const float *__restrict__ conv, int na, int no, int ny, int nx,
+                                                         Anchors8 aw, float *__restrict__ out)
+{
+    extern __shared__ float tile[];   // [no][TP + 1]
+    const int HW = ny * nx, p0 = blockIdx.x * TP;
+    const size_t ba = blockIdx.y;     // b*na + a
+    const int a = (int)(ba % na);
+    const int np = min(TP, HW - p0);
+    const float *src = conv + ba * no * (size_t)HW;
+    for (int i = threadIdx.x; i < no * TP; i += 256) {
+        const int j = i / TP, pp = i - j * TP;
+        if (pp < np) tile[j * (TP + 1) + pp] = decode_box_value(src[(size_t)j * HW + p0 + pp], j, p0 + pp, a, ny, nx, aw.v);
+    }
+    __syncthreads();
+    float *dst = out + (ba * HW + p0) * no;
+    for (int i = threadIdx.x; i < np * no; i += 256) {
+        const int pp = i / no, j = i - pp * no;
+        dst[i] = tile[j * (TP + 1) + pp];
+    }
 }
 
 // host launcher used by yc_head_forward (yc_abi.cu)
@@ -329,9 +344,18 @@ extern "C" int yc_decode_box(const float *conv, int bs, int na, int no, int ny, 
                "yc_decode_box: bad shape");
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < na * 2; ++i) a[i] = anchor_wh_scaled_host[i];
-    const size_t total = (size_t)bs * na * ny * nx * no;
-    decode_box_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        conv, bs, na, no, ny, nx, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], out);
+    Anchors8 aw;
+    for (int i = 0; i < 8; ++i) aw.v[i] = a[i];
+    const int HW = ny * nx;
+    YC_REQUIRE((size_t)bs * na <= 65535, YC_ERR_UNSUPPORTED, "yc_decode_box: bs*na > 65535");
+    if ((size_t)no * 65 * 4 <= 48 * 1024) {
+        decode_box_kernel<64><<<dim3((HW + 63) / 64, bs * na), 256, (size_t)no * 65 * 4, (cudaStream_t)stream>>>(
+            conv, na, no, ny, nx, aw, out);
+    } else {
+        YC_REQUIRE((size_t)no * 9 * 4 <= 48 * 1024, YC_ERR_UNSUPPORTED, "yc_decode_box: no = %d too large", no);
+        decode_box_kernel<8><<<dim3((HW + 7) / 8, bs * na), 256, (size_t)no * 9 * 4, (cudaStream_t)stream>>>(
+            conv, na, no, ny, nx, aw, out);
+    }
     YC_CUDA(cudaGetLastError());
     return YC_OK;
 }

@@ -184,7 +184,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int a = P.ibin ? 0 : e >> 2;       // anchor of the tile handled by this warp (IBin: one anchor per tile)
         float *slab = (float *)((uint8_t *)slabs + (size_t)e * P.slab_bytes);
         const int no = P.no, no_out = P.no_out;
-        int it = 0, cur_lv = -1;
+        int it = 0, cur_key = -1;
         BoxSb sbv;
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
             const TileCoord tc = tile_coord(P, t);
@@ -199,9 +199,11 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const float2 *sb = L.sb + ar * no;
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_MAX_N + a * no);
 
-            if (P.fused && tc.lv != cur_lv) { // fused mode: one anchor group per tile, so `ar` is fixed for this warp
+            // fused mode: the (scale, bias) pairs this warp needs live in registers; they change with the level and,
+            // when the anchors of a pixel block are separate tiles (na*no > 256 columns), with the anchor group
+            if (P.fused && tc.lv * YC_MAX_ANCHORS + tc.g != cur_key) {
                 sbv = load_box_sb(sb, lane, P.nc);
-                cur_lv = tc.lv;
+                cur_key = tc.lv * YC_MAX_ANCHORS + tc.g;
             }
             mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();

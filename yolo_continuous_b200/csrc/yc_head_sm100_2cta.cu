@@ -185,6 +185,13 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                 const int wkey = tc.lv;
                 const bool load_b = !(nkb <= T2_B_SLOTS && resident == wkey);
                 resident = nkb <= T2_B_SLOTS ? wkey : -1;
+                // A weight slot is handed back to the producer by the LAST tile that reads it: a resident weight tile
+                // (all k-blocks in the slots) is read by every following tile of the same level without a reload, so
+                // the release waits for the tile after which the producer loads again (the tile sequence is
+                // deterministic: look one tile ahead).  Streaming levels reuse the slots inside a tile and release
+                // per k-block.  One release per load keeps the producer's phase bookkeeping exact.
+                bool release_b = true;
+                if (nkb <= T2_B_SLOTS && t + n_pairs < P.total_tiles) release_b = box_tile(P, t + n_pairs).lv != wkey;
                 const int buf = it & 1;
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_MAX_N;
                 // both CTAs' epilogues drained the buffer (also orders this warp's tfull arrival after the previous
@@ -199,6 +206,7 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                         const uint64_t da = da0 + (uint64_t)((uint32_t)(sa * T2_A_BYTES) >> 4);
                         const uint64_t db = db0 + (uint64_t)((uint32_t)(s * T2_B_BYTES) >> 4);
                         while (*turn != g) { }
+                        tc_fence_after();   // the other issuer's MMAs (ordered before its `turn` store) precede ours
                         if (elect_one()) {
                             if (!skip_mma) {
 #pragma unroll
@@ -207,9 +215,11 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                                                  db + (uint64_t)(((k / 4) * T2_B_BOX + (k % 4) * 32) >> 4), idesc,
                                                  (uint32_t)((kb | k) != 0));
                             }
+                            tc_fence_before();  // tcgen05 memory model: cross-thread MMA -> MMA order needs the fence pair
+                            __threadfence_block();
                             *turn = g + 1;
                             mma_commit_pair(&R.a_empty[sa]);
-                            if (load_b) mma_commit_pair(&R.b_empty[s]);
+                            if (release_b) mma_commit_pair(&R.b_empty[s]);
                         }
                         __syncwarp();
                     }

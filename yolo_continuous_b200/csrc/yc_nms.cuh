@@ -19,6 +19,7 @@ struct NmsWs {
     int *cursor;                    // [bs*nc]
     int *kept_count;                // [bs*nc]
     int *img_total;                 // [bs] kept detections of an image + 1 once known (0 = not yet): chained scan
+    int *ticket;                    // [1] finish_kernel: CTAs take their work item in the order they start running
     int *seg_off;                   // [bs*nc]
     int *kept_off;                  // [bs*nc]
     size_t counters_bytes;
@@ -44,6 +45,7 @@ static inline NmsWs carve(void *base, int bs, int rows, int nc)
     w.cursor = (int *)take(s * 4);
     w.kept_count = (int *)take(s * 4);
     w.img_total = (int *)take((size_t)bs * 4);
+    w.ticket = (int *)take(4);
     w.counters = (int *)c0;
     w.counters_bytes = (size_t)(p - c0);
     w.seg_off = (int *)take(s * 4);

@@ -376,10 +376,12 @@ __global__ void __launch_bounds__(NMS_NT) nms_segment_kernel(int rows, int nc, f
 }
 
 // ---- K5: per-image finish: kept-count scan, chained scan across images, output assembly -----------------
-// grid = bs.  CTA b scans its image's kept counts, publishes the image total (img_total[b] = total + 1) and
-// obtains its output offset by summing the totals of all earlier images, spinning on the few that are not
-// published yet (earlier CTAs are always scheduled first, so this cannot deadlock).  It then writes the
-// image's rows (reference detect.py:121,137) and optionally undoes the letterbox:
+// grid = bs * slices CTAs.  A CTA takes its work item (image b, slice y) from a ticket counter, i.e. in the order in
+// which CTAs actually start running; slice 0 of image b scans the image's kept counts and publishes the image total
+// (img_total[b] = total + 1).  Every CTA obtains its output offset by summing the totals of all earlier images,
+// waiting for the few that are not published yet: those belong to LOWER tickets, whose CTAs are already running, so the
+// wait cannot starve whatever order the hardware dispatches CTAs in (and whatever else occupies the SMs).  It then
+// writes the image's rows (reference detect.py:121,137) and optionally undoes the letterbox:
 // yolo_correct_boxes (detect.py:140-142,147-165) is evaluated with numpy's promotion rules: binary64 when
 // letterbox_image is set (except box_hw *= scale, rounded back to binary32), binary32 until the final
 // multiply by the image shape otherwise; the result is stored as binary32.
@@ -392,14 +394,18 @@ struct CorrectParams {
 constexpr int FINISH_NT = 256;   // 256 x 47 registers: fits next to a resident head CTA (see TC_MAX_REGS)
 constexpr int FINISH_SMEM_NC = 1024;
 
-__global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int nc, NmsWs ws, int *__restrict__ out_counts,
+__global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int slices, int rows, int nc, NmsWs ws, int *__restrict__ out_counts,
                                                             int *__restrict__ out_offsets, float *__restrict__ out_rows,
                                                             int *__restrict__ out_idx, CorrectParams cp)
 {
     __shared__ int s_red[FINISH_NT / 32];
     __shared__ int s_total, s_base;
     __shared__ int s_koff[FINISH_SMEM_NC + 1], s_soff[FINISH_SMEM_NC];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(ws.ticket, 1);
+    __syncthreads();
+    const int b = s_ticket / slices, slice = s_ticket - b * slices;
     const size_t sb = (size_t)b * nc;
     const bool flat = nc <= FINISH_SMEM_NC;
     // exclusive scan of kept_count[b][:] -> kept_off (warp 0, 32 classes per step)
@@ -423,7 +429,7 @@ __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int
         if (lane == 0) {
             s_total = running;
             if (flat) s_koff[nc] = running;
-            if (blockIdx.y == 0) atomicExch(&ws.img_total[b], running + 1); // publish
+            if (slice == 0) atomicExch(&ws.img_total[b], running + 1); // publish
         }
     }
     // chained scan: sum of the totals of images 0..b-1
@@ -441,7 +447,7 @@ __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int
         int base = 0;
         for (int w = 0; w < FINISH_NT / 32; ++w) base += s_red[w];
         s_base = base;
-        if (blockIdx.y == 0) {
+        if (slice == 0) {
             out_counts[b] = s_total;
             out_offsets[b] = base;
             if (b == bs - 1) out_offsets[bs] = base + s_total;
@@ -449,7 +455,7 @@ __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int
     }
     __syncthreads(); // also makes warp 0's kept_off writes visible to the block
     const int img_base = s_base;
-    if (s_total == 0 || (int)blockIdx.y * FINISH_NT >= s_total) return;
+    if (s_total == 0 || slice * FINISH_NT >= s_total) return;
 
     double off[2] = {0, 0}, scl[2] = {1, 1}, ims[2] = {1, 1};
     if (cp.enabled) {
@@ -499,10 +505,10 @@ __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int
         o[4] = oc.x; o[5] = oc.y; o[6] = (float)c;
         out_idx[oidx] = row;
     };
-    // gridDim.y CTAs share the rows of an image (one per image at detection thresholds; several when most of the
-    // 25 200 rows of a low-threshold image survive): slice y takes the k with (k / FINISH_NT) % gridDim.y == y
+    // `slices` CTAs share the rows of an image (one per image at detection thresholds; several when most of the
+    // 25 200 rows of a low-threshold image survive): slice y takes the k with (k / FINISH_NT) % slices == y
     if (flat) {
-        for (int k = blockIdx.y * FINISH_NT + tid; k < total; k += FINISH_NT * gridDim.y) {
+        for (int k = slice * FINISH_NT + tid; k < total; k += FINISH_NT * slices) {
             int lo = 0, hi = nc; // last c with s_koff[c] <= k (empty classes share their successor's offset)
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(FINISH_NT) finish_kernel(int bs, int rows, int
             write_row(lo, ws.kept_row[ib + s_soff[lo] + (k - s_koff[lo])], (size_t)img_base + k);
         }
     } else {
-        for (int c = wid + blockIdx.y * (FINISH_NT / 32); c < nc; c += (FINISH_NT / 32) * gridDim.y) {
+        for (int c = wid + slice * (FINISH_NT / 32); c < nc; c += (FINISH_NT / 32) * slices) {
             const int nk = ws.kept_count[sb + c];
             if (nk == 0) continue;
             const int *kept_row = ws.kept_row + ib + ws.seg_off[sb + c];
@@ -554,13 +560,12 @@ int launch_nms_tail(const yc_nms_params *p, const NmsWs &ws, float *out_rows, in
     nms_segment_kernel<<<dim3((p->nc + spc - 1) / spc, p->bs), NMS_NT, 0, stream>>>(p->rows, p->nc,
                                                                                      thr_to_f32_floor(p->nms_thres), spc, ws);
     CorrectParams cp{p->correct_boxes, p->letterbox, p->input_h, p->input_w, (const int *)p->image_hw, p->image_hw_stride};
-    // slices per image: enough CTAs to cover the GPU when the batch alone does not (the chained scan over images needs
-    // the y == 0 CTAs of all earlier images to be scheduled first: x is the fastest grid dimension, so they are)
+    // slices per image: enough CTAs to cover the GPU when the batch alone does not
     int slices = 1;
     if (p->bs < 32)
         while (slices < 16 && (long long)p->bs * slices < 148 && (long long)slices * FINISH_NT * 4 < p->rows) slices *= 2;
-    finish_kernel<<<dim3(p->bs, slices), FINISH_NT, 0, stream>>>(p->bs, p->rows, p->nc, ws, out_counts, out_offsets, out_rows,
-                                                               out_idx, cp);
+    finish_kernel<<<p->bs * slices, FINISH_NT, 0, stream>>>(p->bs, slices, p->rows, p->nc, ws, out_counts, out_offsets,
+                                                            out_rows, out_idx, cp);
     YC_CUDA(cudaGetLastError());
     return YC_OK;
 }

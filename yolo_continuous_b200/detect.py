@@ -52,13 +52,14 @@ def decode_box(inputs, anchors, anchors_mask, num_labels, image_size=(640, 640))
 
 
 def nms_device(prediction, num_classes, conf_thres, nms_thres, input_shape=None, image_shape=None,
-               letterbox_image=False, write_corners=True):
+               letterbox_image=False, write_corners=True, box_div=None):
     """Batched threshold + per-class NMS on the device, results left on the device.
 
     Returns (rows [total,7], idx [total] original row per detection, counts [bs], offsets [bs+1]),
     all CUDA tensors; rows/idx are views of a capacity-sized buffer (valid up to offsets[bs]).
     With image_shape given the rows hold y1,x1,y2,x2 in image pixels (yolo_correct_boxes), else
-    x1,y1,x2,y2 as decoded.
+    x1,y1,x2,y2 as decoded.  box_div = (w, h): cx,w /= w and cy,h /= h (IEEE division) before the corners are formed
+    (`box_div_w/h` of yc_nms_params: IDetect's input-pixel boxes -> the normalised boxes yolo_correct_boxes expects).
     """
     _lib.require_cuda(prediction, "prediction")
     if prediction.dtype != torch.float32 or prediction.dim() != 3 or not prediction.is_contiguous():
@@ -69,6 +70,8 @@ def nms_device(prediction, num_classes, conf_thres, nms_thres, input_shape=None,
     p.bs, p.rows, p.row_stride, p.nc = bs, rows, stride, num_classes
     p.conf_thres, p.nms_thres = float(conf_thres), float(nms_thres)
     p.write_corners = 1 if write_corners else 0
+    if box_div is not None:
+        p.box_div_w, p.box_div_h = float(box_div[0]), float(box_div[1])
     hw = None
     if image_shape is not None:
         p.correct_boxes, p.letterbox = 1, 1 if letterbox_image else 0
@@ -91,13 +94,13 @@ def nms_device(prediction, num_classes, conf_thres, nms_thres, input_shape=None,
 
 
 def non_max_suppression(prediction, num_classes, input_shape, image_shape, letterbox_image,
-                        conf_thres=0.5, nms_thres=0.4, return_indices=False):
+                        conf_thres=0.5, nms_thres=0.4, return_indices=False, box_div=None):
     """Reference detect.py:90-144.  prediction [bs, rows, 5+nc] (xywh + obj + cls) on a CUDA device;
     its first four columns are overwritten with corners, as the reference does (detect.py:103).
     Returns a list with, per image, None or ndarray[n,7] = y1,x1,y2,x2 (image px), obj, class_conf,
     class_id -- classes ascending, score descending within a class."""
     rows, idx, counts, offsets = nms_device(prediction, num_classes, conf_thres, nms_thres, input_shape,
-                                            image_shape, letterbox_image, write_corners=True)
+                                            image_shape, letterbox_image, write_corners=True, box_div=box_div)
     off = offsets.cpu().numpy()
     total = int(off[-1])
     host = rows[:total].cpu().numpy()
@@ -185,7 +188,5 @@ def detect_post_backbone(head, features, input_shape, image_shape, letterbox_ima
         z, _ = head(list(features))
     finally:
         head.return_raw = was
-    scale = torch.tensor([input_shape[1], input_shape[0], input_shape[1], input_shape[0]], dtype=torch.float32,
-                         device=z.device)
-    z[..., :4] /= scale
-    return non_max_suppression(z, head.nc, input_shape, image_shape, letterbox_image, conf_thres, nms_thres)
+    return non_max_suppression(z, head.nc, input_shape, image_shape, letterbox_image, conf_thres, nms_thres,
+                               box_div=(input_shape[1], input_shape[0]))

@@ -79,6 +79,7 @@ class PostBackbone:
                 lv.anchor_wh[j] = v
         d.z = self.z.data_ptr()
         self.desc = d
+        self._weight_key = self._weights_version()
         p = _lib.NmsParams()
         p.bs, p.rows, p.row_stride, p.nc = bs, self.rows, self.no, self.nc
         p.conf_thres, p.nms_thres = float(conf_thres), float(nms_thres)
@@ -107,6 +108,33 @@ class PostBackbone:
                                                                C.c_void_p(self.tail_stream.cuda_stream)),
                                "yc_nms_workspace_reset")
                     self.ev_tail[i].record(self.tail_stream)
+
+    # ---- head parameters: the packed blobs follow the parameters' version counters --------------------------------
+    def _weights_version(self):
+        h = self.head
+        return tuple(p._version for i in range(self.nl)
+                     for p in (h.m[i].weight, h.m[i].bias, h.ia[i].implicit, h.im[i].implicit) if p is not None)
+
+    def refresh_weights(self, force=False):
+        """Re-pack the head parameters if they changed since the descriptor was built (in-place updates, e.g.
+        load_state_dict, bump the version counters checked here on every call; call with force=True after replacing
+        parameter tensors).  Captured graphs are dropped: they hold the old blob pointers."""
+        key = self._weights_version()
+        if not force and key == self._weight_key:
+            return False
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)    # work in flight still reads the old blobs
+            if force:
+                self.head._packed.clear()
+            self._blobs = []
+            for i in range(self.nl):
+                blob = self.head._blob((id(self.head.m[i]),), self.head.m[i], self.head.ia[i], self.head.im[i], self.device)
+                self._blobs.append(blob)
+                self.desc.level[i].blob = blob.data_ptr()
+        self._graphs.clear()
+        self._pgraphs.clear()
+        self._weight_key = key
+        return True
 
     @property
     def ws(self):
@@ -207,7 +235,10 @@ class PostBackbone:
         """features: list of [bs, ch_i, H_i, W_i] device tensors.  Returns device views
         (rows [bs*rows,7] capacity, idx, counts [bs], offsets [bs+1]); with overlap=True they are complete once
         `done_event` has fired (`wait()` orders the current stream behind it)."""
+        self.refresh_weights()
         with torch.cuda.device(self.device):
+            if self._in_flight:
+                raise _lib.YcError("run_device() while a submit() batch is in flight: call drain() first")
             if self.n_bufs > 1:
                 self.cur ^= 1
             ptrs = tuple(x.data_ptr() for x in features) + (self.cur,)
@@ -239,6 +270,7 @@ class PostBackbone:
         tensors (graphs are keyed by the input pointers)."""
         if not (self.overlap and self.fused):
             raise _lib.YcError("submit() needs overlap=True and the fused step")
+        self.refresh_weights()
         with torch.cuda.device(self.device):
             if self._eager_dirty:   # order behind NMS kernels an earlier run_device() left on the tail stream
                 torch.cuda.current_stream().wait_event(self.ev_tail[0])
@@ -247,7 +279,10 @@ class PostBackbone:
             prev = self.cur if self._in_flight else None
             self.cur ^= 1
             c = self.cur
-            key = tuple(x.data_ptr() for x in features) + (c,)
+            # The first step of a stream of batches has no previous batch: its graph carries the head kernel only, so
+            # that results an earlier eager run_device() call left in the other output buffer stay untouched
+            with_tail = self._in_flight
+            key = tuple(x.data_ptr() for x in features) + (c, with_tail)
             g = self._pgraphs.get(key)
             if g is None:
                 for i, x in enumerate(features):
@@ -258,7 +293,7 @@ class PostBackbone:
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
-                    self._pipelined_step(features, c)
+                    self._pipelined_step(features, c, with_tail)
                 if len(self._pgraphs) > 16:
                     self._pgraphs.clear()
                 self._pgraphs[key] = g
@@ -289,19 +324,21 @@ class PostBackbone:
         _lib.check(_lib.lib.yc_nms_workspace_reset(C.byref(self.nms_params), self.wss[c].data_ptr(), self.wss[c].numel(), sp),
                    "yc_nms_workspace_reset")
 
-    def _pipelined_step(self, features, c):
+    def _pipelined_step(self, features, c, with_tail=True):
         """(captured) head of the current batch into workspace c  ||  NMS kernels of the previous batch (workspace
-        1-c; an all-zero workspace on the very first step yields zero detections)."""
+        1-c); with_tail=False (first step of a stream of batches): the head kernel only."""
         main = torch.cuda.current_stream()
         side = self.tail_stream
-        side.wait_stream(main)                                   # fork
+        if with_tail:
+            side.wait_stream(main)                               # fork
         for i, x in enumerate(features):
             self.desc.level[i].x = x.data_ptr()
         _lib.check(_lib.lib.yc_detect_fused_head_noreset(C.byref(self.desc), C.byref(self.nms_params),
                                                          self.wss[c].data_ptr(), self.wss[c].numel(),
                                                          C.c_void_p(main.cuda_stream)), "yc_detect_fused_head")
-        self._tail(1 - c, side)
-        main.wait_stream(side)                                   # join
+        if with_tail:
+            self._tail(1 - c, side)
+            main.wait_stream(side)                               # join
 
     # ---- host path (the e2e call) -----------------------------------------------------------------
     def run_host(self, features_host=None):
