@@ -53,6 +53,7 @@ def sd_np(head, prefix):
 
 
 def head_case(cls, name, nc, anchors, ch, shapes, bs, seed, **kw):
+    torch.manual_seed(seed)   # default-initialised parameters (conv biases) come from the global generator
     gen = torch.Generator().manual_seed(seed)
     head = cls(nc, anchors, ch, **kw).eval()
     head.stride = torch.tensor(STRIDES)
@@ -157,6 +158,8 @@ def nms_case(name, pred, nc, conf, iou, input_shape, image_shape, letterbox):
 
 
 def main():
+    torch.manual_seed(0)
+    np.random.seed(0)
     # --- a12: the reference's only known-answer data, utils/bbox.py:207-225 ---------------
     xxyy = torch.asarray([[1, 2, 3, 5]]).float()
     kat = {"xxyy": xxyy.numpy()}
@@ -237,6 +240,7 @@ def main():
     import copy
     from nets.common import RepConv
     for name, (c1, c2, s_) in (("repconv_identity", (8, 8, 1)), ("repconv_noid", (6, 10, 2))):
+        torch.manual_seed(31)   # RepConv's conv weights keep their default initialisation (global generator)
         gen = torch.Generator().manual_seed(31)
         rep = RepConv(c1, c2, 3, s_).eval()
         for m_ in rep.modules():
