@@ -1,4 +1,4 @@
-"""torch-CPU restatement of the reference's post-backbone path (TEST / BASELINE INFRASTRUCTURE ONLY).
+"""torch restatement of the reference's post-backbone path (TEST / BASELINE INFRASTRUCTURE ONLY).
 
 The reference is pure Python over torch + torchvision, so its own CPU path *is* a sequence of torch
 CPU ops.  /root/reference does not exist on the GPU box, therefore bench.py's `cpu_baseline` and
@@ -8,6 +8,9 @@ CPU ops.  /root/reference does not exist on the GPU box, therefore bench.py's `c
   detect.yolo_correct_boxes  detect.py:147-165
 written from the survey's description, not copied.  tests/test_oracle_golden.py pins it against the
 fixtures generated from the unmodified reference (bit-exact: same ops, same library).
+The ops are device-agnostic, as the reference's are: fed CUDA tensors it runs cuDNN/cuBLAS convolutions, ~50 elementwise
+launches per forward and torchvision's CUDA nms kernels with the reference's per-image / per-class Python loops and
+host round trips (detect.py:124 `.cpu().unique()`, :140 `.cpu().numpy()`) -- bench.py's `library_baseline`.
 Never imported by the product package.
 """
 import numpy as np
@@ -17,7 +20,8 @@ from torchvision.ops import nms as tv_nms
 
 def idetect_forward(p, xs, strides):
     """p: dict with per-level 'w' [N,K], 'b', 'ia', 'im' (numpy or tensors) and 'anchors' [nl,na,2]."""
-    anchors = torch.as_tensor(np.asarray(p["anchors"]), dtype=torch.float32)
+    dev = torch.as_tensor(xs[0]).device
+    anchors = torch.as_tensor(np.asarray(p["anchors"]), dtype=torch.float32).to(dev)
     nl, na = anchors.shape[0], anchors.shape[1]
     zs, raws = [], []
     for i in range(nl):
@@ -30,7 +34,7 @@ def idetect_forward(p, xs, strides):
         t = t.view(bs, na, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
         raws.append(t)
         gy, gx = torch.meshgrid([torch.arange(ny), torch.arange(nx)], indexing="ij")
-        grid = torch.stack((gx, gy), 2).view(1, 1, ny, nx, 2).float()
+        grid = torch.stack((gx, gy), 2).view(1, 1, ny, nx, 2).float().to(dev)   # nets/idetect.py:38 `.to(x[i].device)`
         y = t.sigmoid()
         y[..., 0:2] = (y[..., 0:2] * 2. - 0.5 + grid) * float(strides[i])
         y[..., 2:4] = (y[..., 2:4] * 2) ** 2 * anchors[i].view(1, na, 1, 1, 2)
@@ -68,12 +72,12 @@ def non_max_suppression(prediction, num_classes, input_shape, image_shape, lette
         if not img.size(0):
             continue
         det = torch.cat((img[:, :5], conf.float(), cls.float()), 1)
-        for c in det[:, -1].unique():
+        for c in det[:, -1].cpu().unique():                  # detect.py:124
             dc = det[det[:, -1] == c]
             k = tv_nms(dc[:, :4], dc[:, 4] * dc[:, 5], nms_thres)
             out[i] = dc[k] if out[i] is None else torch.cat((out[i], dc[k]))
         if out[i] is not None:
-            o = out[i].numpy()
+            o = out[i].cpu().numpy()                         # detect.py:140
             xy, wh = (o[:, 0:2] + o[:, 2:4]) / 2, o[:, 2:4] - o[:, 0:2]
             o[:, :4] = correct_boxes(xy, wh, input_shape, image_shape, letterbox_image)
             out[i] = o
