@@ -50,7 +50,8 @@ enum yc_head_kind {
 /* which kernel family runs the 1x1 conv */
 enum yc_head_path {
     YC_PATH_AUTO = 0,    /* tcgen05 when the shape allows it, else generic */
-    YC_PATH_TCGEN05 = 1, /* sm_100a tcgen05/TMEM/TMA kernel; YC_ERR_UNSUPPORTED if the shape does not fit */
+    YC_PATH_TCGEN05 = 1, /* sm_100a tcgen05/TMEM/TMA kernels (bf16 maps: one bf16 MMA per k-step; float32 maps: three fp16
+                            MMAs per k-step on a hi/lo split); YC_ERR_UNSUPPORTED if the shape does not fit */
     YC_PATH_GENERIC = 2  /* any-shape FFMA kernel (exact binary32 accumulation) */
 };
 
@@ -64,8 +65,11 @@ YC_API int yc_device_check(int dev);
  * (nets/idetect.py:21-24, nets/common.py:416-439): ImplicitA is folded into the bias
  * (b' = b + W.ia, binary64 accumulation), ImplicitM stays a per-channel epilogue scale.
  * yc_head_pack writes one blob per level:
- *   [bias2 f32 Npad][scale f32 Npad][scale_split f32 Npad][w32 f32 N*K]
- *   [w_hi f16 Npad*K][w_lo f16 Npad*K][w_bf16 Npad*K]          (Npad = N rounded up to 16)
+ *   [bias2 f32 Npad][scale f32 Npad][scale_split f32 Npad][(scale,bias2) f32x2 Npad][(scale_split,bias2) f32x2 Npad]
+ *   [w32 f32 N*K][w_hi_t f16 K*Npad][w_lo_t f16 K*Npad][w_bf16 Npad*K]          (Npad = N rounded up to 16)
+ * w_hi_t + w_lo_t = W[c,:] * 2^shift(c), split into two fp16 numbers and stored transposed: the operands of the
+ * float32-grade tensor-core path (three fp16 MMAs per k-step, see csrc/yc_head_sm100_split.cu); scale_split undoes the
+ * row scaling and the activation scaling.
  * W [N,K] f32 row-major (Conv2d weight [N,K,1,1]); bias [N] or NULL; ia [K] or NULL; im [N] or NULL.
  */
 YC_API size_t yc_head_pack_bytes(int N, int K);
@@ -87,8 +91,9 @@ typedef struct yc_head_level {
 typedef struct yc_head_desc {
     int32_t kind;      /* yc_head_kind */
     int32_t path;      /* yc_head_path */
-    int32_t x_dtype;   /* yc_dtype of the feature maps: YC_F32 -> fp32-grade result (fp16 hi/lo split
-                          on tensor cores, or exact FFMA on the generic path); YC_BF16 -> bf16 MMA */
+    int32_t x_dtype;   /* yc_dtype of the feature maps: YC_F32 -> float32-grade result (1e-5 parity: fp16 hi/lo split of
+                          both operands on the tensor cores, |x| < 2^20; or exact FFMA on the generic path);
+                          YC_BF16 -> bf16 MMA (1e-3 parity) */
     int32_t nl, na, no; /* levels, anchors per level, conv outputs per anchor (85; IBin 127) */
     int32_t bin_count;  /* IBin only (21) */
     int32_t bs;

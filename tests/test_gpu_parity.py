@@ -843,8 +843,8 @@ def test_fused_pair_kernel_vs_oracle_c2_shapes():
     scale = box_scale(p["anchors"], [8.0, 16.0, 32.0], C2_SHAPES, head.na, 85)
     assert_close_scaled(z.cpu().numpy(), z_ref, scale, RTOL_BF16, "tcgen05 forward @ C2 shapes")
     assert_close_scaled(z.cpu().numpy(), z_ref, scale, 1e-4, "tcgen05 forward @ C2 shapes (tight)")
-    for i in range(3):
-        np.testing.assert_allclose(raws[i].cpu().numpy(), raw_ref[i], rtol=0, atol=1e-4)
+    for i in range(3):   # class logits reach |t| ~ 10: the accumulation noise is relative
+        np.testing.assert_allclose(raws[i].cpu().numpy(), raw_ref[i], rtol=1e-4, atol=1e-4)
     # (2) fused step: CTA-pair kernel (default) and the 1-CTA kernel (YC_TC_2CTA=0), eager and pipelined graphs
     import os
     for two_cta in ("1", "0"):
@@ -956,3 +956,59 @@ def test_pipeline_follows_weight_updates_and_keeps_eager_results():
     r = pipe.drain()
     torch.cuda.synchronize()
     assert int(r[3][-1]) == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# float32 feature maps on the tensor cores (fp16 hi/lo split, yc_head_sm100_split.cu): 1e-5 parity
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["idetect", "iaux", "ibin"])
+def test_tcgen05_fp32_split_vs_oracle(kind):
+    """Forced tcgen05 path with float32 maps (reference precision, nets/idetect.py:31): COCO channel counts (K = 256 / 512 /
+    1024: the longest accumulation chains), ragged pixel tiles, against the oracle at the float32 tolerance."""
+    from yolo_continuous_b200 import _lib
+    mult = 2 if kind == "iaux" else 1
+    ch = (256, 512, 1024) * mult
+    shapes = [(12, 20), (6, 12), (4, 6)] * mult
+    head, xs = _random_head_case(kind, 80, ch, shapes, 3, 19, torch.float32)
+    xs = [x * 3.0 for x in xs]   # a wider range of magnitudes (|x| up to ~15) than N(0,1)
+    p = _oracle_params(head, kind, False)
+    res = orc.head_forward(kind, p, [x.numpy() for x in xs], [8.0, 16.0, 32.0])
+    head = head.to(DEV)
+    head.head_path = _lib.YC_PATH_TCGEN05
+    lst = [x.to(DEV) for x in xs]
+    z, raws = head(lst)
+    scale = box_scale(p["anchors"], [8.0, 16.0, 32.0], shapes[:3], head.na, z.shape[-1])
+    zc = z.cpu().numpy()
+    if kind == "ibin":
+        zc, n_ties = _ibin_accept_exact_ties(zc, res[0], res[1], p["anchors"], p["bins_w"], p["bin_count"], scale, RTOL_F32,
+                                             4e-6, "tcgen05-fp32/ibin")
+        assert n_ties < 1e-3 * zc[..., 2:4].size
+    assert_close_scaled(zc, res[0], scale, RTOL_F32, f"tcgen05-fp32/{kind}")
+    for i in range(head.nl):   # raw logits: |a-b| <= 1e-5 * max(|ref|, 1)
+        r, want = raws[i].cpu().numpy(), res[1][i]
+        assert np.all(np.abs(r - want) <= 1e-5 * np.maximum(np.abs(want), 1.0)), float(np.abs(r - want).max())
+    if kind == "iaux":
+        for i in range(head.nl):
+            r, want = lst[i + head.nl].cpu().numpy(), res[2][i]
+            assert np.all(np.abs(r - want) <= 1e-5 * np.maximum(np.abs(want), 1.0))
+    head.return_raw = False
+    z2, _ = head([x.to(DEV) for x in xs])
+    if kind != "ibin":
+        assert torch.equal(z2, z)
+
+
+def test_tcgen05_fp32_split_full_size_vs_exact_kernel():
+    """COCO head at 640x640, float32 maps, bs 4: the tensor-core split path against the exact-FFMA kernel."""
+    from yolo_continuous_b200 import _lib
+    head, _ = _random_head_case("idetect", 80, (256, 512, 1024), [(1, 8)] * 3, 1, 13, torch.float32)
+    head = head.to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(4321)
+    xs = [torch.randn(4, c, s, s, generator=g, device=DEV) for c, s in zip((256, 512, 1024), (80, 40, 20))]
+    head.head_path = _lib.YC_PATH_GENERIC
+    z_g, raw_g = head(list(xs))
+    head.head_path = _lib.YC_PATH_TCGEN05
+    z_t, raw_t = head(list(xs))
+    for a_, b_ in zip(raw_t, raw_g):
+        assert float(((a_ - b_).abs() / b_.abs().clamp_min(1.0)).max()) < 1e-5
+    rel = (z_t - z_g).abs() / z_g.abs().clamp_min(8.0)
+    assert float(rel.max()) < 1e-5

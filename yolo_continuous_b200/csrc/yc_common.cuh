@@ -32,16 +32,21 @@ int cuda_fail(cudaError_t e, const char *what);
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline size_t round_up_sz(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+// float32 maps on the tensor cores (yc_head_sm100_split.cu): activations are scaled by 2^-YC_SPLIT_XSHIFT before they are
+// split into two fp16 numbers (range +-65504 * 2^XSHIFT ~ 1e6; the low part of |x| < 2 is a subnormal, absolute error
+// <= 2^-25 * 2^XSHIFT); the epilogue scale carries the inverse
+#define YC_SPLIT_XSHIFT 4
+
 // ---- blob layout produced by yc_head_pack (see include/yc_b200.h) ------------------------
 struct BlobView {
     const float *bias2;       // im * (b + W.ia)
     const float *scale;       // im
-    const float *scale_split; // im * 2^-shift(c)   (fp16 hi/lo path)
+    const float *scale_split; // im * 2^(YC_SPLIT_XSHIFT - shift(c))   (fp16 hi/lo path)
     const float2 *sb;         // (scale, bias2) interleaved: one 8-byte broadcast load per column in the epilogue
     const float2 *sb_split;   // (scale_split, bias2)
     const float *w32;         // [N,K]
-    const __half *w_hi;       // [Npad,K]  fp16(W * 2^shift)
-    const __half *w_lo;       // [Npad,K]  fp16(W * 2^shift - w_hi)
+    const __half *w_hi_t;     // [K,Npad]  fp16(W * 2^shift(c)), transposed (MN-major B operand)
+    const __half *w_lo_t;     // [K,Npad]  fp16(W * 2^shift(c) - w_hi)
     const __nv_bfloat16 *w_bf; // [Npad,K]
 };
 
@@ -62,8 +67,8 @@ __host__ __device__ inline BlobView blob_view(const void *blob, int N, int K)
     v.w32 = (const float *)p;                    p += w32b;
     size_t w16b = sizeof(__half) * (size_t)Npad * K;
     w16b = (w16b + 127) / 128 * 128;
-    v.w_hi = (const __half *)p;                  p += w16b;
-    v.w_lo = (const __half *)p;                  p += w16b;
+    v.w_hi_t = (const __half *)p;                p += w16b;
+    v.w_lo_t = (const __half *)p;                p += w16b;
     v.w_bf = (const __nv_bfloat16 *)p;
     return v;
 }

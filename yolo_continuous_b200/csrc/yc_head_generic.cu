@@ -2,7 +2,8 @@
 //
 //  * yc_head_pack: folds ImplicitA into the bias (reference nets/common.py:425-426 applied before the
 //    conv at nets/idetect.py:31), keeps ImplicitM (nets/common.py:438-439) as an epilogue scale and
-//    produces the operand formats of the tcgen05 kernel (bf16; fp16 hi/lo split with per-row scaling).
+//    produces the operand formats of the tcgen05 kernels (bf16 for bf16 maps; a per-row scaled fp16 hi/lo split,
+//    transposed, for float32 maps: yc_head_sm100_split.cu).
 //  * head_generic_kernel: FFMA-tiled 1x1 conv with exact binary32 accumulation and the decode fused in
 //    the epilogue.  It is the path for shapes the TMA/tcgen05 kernel cannot take (feature-map rows
 //    not 16-byte multiples, na*no > 256, K % 16 != 0) and the on-device cross-check of that kernel.
@@ -22,8 +23,8 @@ __global__ void __launch_bounds__(128) head_pack_kernel(const float *__restrict_
     if (c >= Npad) return;
     if (c >= N) { // zero padding rows: the MMA sees zeros, the epilogue never reads them
         for (int k = lane; k < K; k += 32) {
-            w_hi[(size_t)c * K + k] = __float2half_rn(0.f);
-            w_lo[(size_t)c * K + k] = __float2half_rn(0.f);
+            w_hi[(size_t)k * Npad + c] = __float2half_rn(0.f);
+            w_lo[(size_t)k * Npad + c] = __float2half_rn(0.f);
             w_bf[(size_t)c * K + k] = __float2bfloat16_rn(0.f);
         }
         if (lane == 0) {
@@ -56,8 +57,8 @@ __global__ void __launch_bounds__(128) head_pack_kernel(const float *__restrict_
         const float ws = w * up; // exact (power of two)
         const __half hi = __float2half_rn(ws);
         const __half lo = __float2half_rn(ws - __half2float(hi));
-        w_hi[(size_t)c * K + k] = hi;
-        w_lo[(size_t)c * K + k] = lo;
+        w_hi[(size_t)k * Npad + c] = hi;   // transposed: the split kernel reads the weights as an MN-major operand
+        w_lo[(size_t)k * Npad + c] = lo;
         w_bf[(size_t)c * K + k] = __float2bfloat16_rn(w);
         w32[(size_t)c * K + k] = w;
     }
@@ -66,9 +67,9 @@ __global__ void __launch_bounds__(128) head_pack_kernel(const float *__restrict_
         const float m = im ? im[c] : 1.0f;
         bias2[c] = __fmul_rn(m, b1);
         scale[c] = m;
-        scale_split[c] = ldexpf(m, -shift);
+        scale_split[c] = ldexpf(m, YC_SPLIT_XSHIFT - shift);
         sb[c] = make_float2(m, __fmul_rn(m, b1));
-        sb_split[c] = make_float2(ldexpf(m, -shift), __fmul_rn(m, b1));
+        sb_split[c] = make_float2(ldexpf(m, YC_SPLIT_XSHIFT - shift), __fmul_rn(m, b1));
     }
 }
 
@@ -331,7 +332,7 @@ extern "C" int yc_head_pack(const float *W, const float *bias, const float *ia, 
     head_pack_kernel<<<(Npad + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
         W, bias, ia, im, N, K, Npad, (float *)v.bias2, (float *)v.scale, (float *)v.scale_split, (float2 *)v.sb, (float2 *)v.sb_split,
         (float *)v.w32,
-        (__half *)v.w_hi, (__half *)v.w_lo, (__nv_bfloat16 *)v.w_bf);
+        (__half *)v.w_hi_t, (__half *)v.w_lo_t, (__nv_bfloat16 *)v.w_bf);
     YC_CUDA(cudaGetLastError());
     return YC_OK;
 }

@@ -183,7 +183,6 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int q = warp & 3;     // TMEM lane quadrant this warp may read
         const int a = P.ibin ? 0 : e >> 2;       // anchor of the tile handled by this warp (IBin: one anchor per tile)
         float *slab = (float *)((uint8_t *)slabs + (size_t)e * P.slab_bytes);
-        const int no = P.no, no_out = P.no_out;
         int it = 0, cur_key = -1;
         BoxSb sbv;
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
@@ -192,12 +191,9 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const int buf = it & 1;
             const int prow0 = tc.p0 + 32 * q;            // first pixel of this warp's 32 rows
             const int nv = min(32, L.HW - prow0);        // valid rows (<= 0: nothing to store)
-            const int p = prow0 + lane;
-            const float gx = (float)(p % L.nx), gy = (float)(p / L.nx);
             const int ar = tc.g * P.na + a;               // anchor of the head this warp decodes
-            const float aw = L.anchor_wh[2 * ar], ah = L.anchor_wh[2 * ar + 1];
-            const float2 *sb = L.sb + ar * no;
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_MAX_N + a * no);
+            const float2 *sb = L.sb + ar * P.no;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_MAX_N + a * P.no);
 
             // fused mode: the (scale, bias) pairs this warp needs live in registers; they change with the level and,
             // when the anchors of a pixel block are separate tiles (na*no > 256 columns), with the anchor group
@@ -217,64 +213,8 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane, sbv);
                 continue;
             }
-            if (P.ibin) {
-                // IBin (nets/ibin.py:56-72): 127 accumulator columns and as many sigmoids per row made this epilogue the
-                // bottleneck with one warp per quadrant (1.28 ms against 0.30 ms with the epilogue switched off), so
-                // the three warps of a quadrant split the columns [x y | w bins | h bins] [obj + half of the classes]
-                // [rest] and fill ONE slab per quadrant, which the first of them stores.
-                const int part = e >> 2;
-                const int len = P.bin_count + 1, s1 = 2 + 2 * len;       // s1: objectness column
-                const int sc = s1 + (no - s1) / 3;                       // classes are shared 1/3 : 2/3 by parts 1 and 2
-                float *zs = (float *)((uint8_t *)slabs + (size_t)q * P.slab_bytes), *rs = zs + 32 * no_out;
-                if (part == 0) {
-                    if (lane == 0) bulk_wait_read0();   // the previous stores from this quadrant's slab have been read out
-                    __syncwarp();
-                }
-                named_bar_sync(1 + q, 96);
-                // part 0: [x y | w block]   part 1: [h block] + objectness and a third of the classes   part 2: the rest
-                const int cb = part == 0 ? 0 : (part == 1 ? 2 + len : sc), ce = part == 0 ? 2 + len : (part == 1 ? sc : no);
-                if (L.raw) epi_range_raw(taddr, cb, ce, sb, rs + lane * no);
-                if (P.write_z) {
-                    float *zrow = zs + lane * no_out;
-                    if (part == 0) epi_range_ibin(taddr, 0, 2 + len, true, false, sb, zrow, gx, gy, L.stride, L.stride_y, aw, ah, P);
-                    if (part == 1) {
-                        epi_range_ibin(taddr, 2 + len, s1, false, true, sb, zrow, gx, gy, L.stride, L.stride_y, aw, ah, P);
-                        epi_range_sig(taddr, s1, sc, sb, zrow, 2 * len - 2);
-                    }
-                    if (part == 2) epi_range_sig(taddr, sc, no, sb, zrow, 2 * len - 2);
-                }
-                tc_fence_before();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-                named_bar_sync(5 + q, 96);              // all three parts of the rows are in the slab
-                if (part == 0 && nv > 0) {
-                    if (L.raw) slab_store(L.raw + (((size_t)tc.b * P.na_real + ar) * L.HW + prow0) * no, rs, nv, no, lane);
-                    if (P.write_z)
-                        slab_store(P.z + ((size_t)tc.b * P.rows_total + L.row_off + (size_t)ar * L.HW + prow0) * no_out, zs, nv,
-                                   no_out, lane);
-                }
-                continue;
-            }
-            if (L.raw) {
-                if (lane == 0) bulk_wait_read0(); // previous store from this slab has been read out
-                __syncwarp();
-                epi_row<true>(taddr, no, sb, slab + lane * no, gx, gy, L.stride, L.stride_y, aw, ah);
-                if (nv > 0)
-                    slab_store(L.raw + (((size_t)tc.b * P.na_real + ar) * L.HW + prow0) * no, slab, nv, no, lane);
-            }
-            if (P.write_z) {
-                if (lane == 0) bulk_wait_read0();
-                __syncwarp();
-                epi_row<false>(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, L.stride_y, aw, ah);
-            }
-            // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-            if (P.write_z && nv > 0)
-                slab_store(P.z + ((size_t)tc.b * P.rows_total + L.row_off + (size_t)ar * L.HW + prow0) * no_out, slab, nv,
-                           no_out, lane);
+            store_epilogue<false>(P, L, tc.b, tc.p0, tc.g, e, q, lane, tmem_base + (uint32_t)(buf * TC_MAX_N), (uint8_t *)slabs,
+                                  &tempty_bar[buf]);
         }
         if (lane == 0) bulk_wait_all0(); // global writes complete before the CTA exits
     }
@@ -315,6 +255,8 @@ int set_reserved_sms(int n)
 }
 
 int launch_head_tc2(const TcMaps &maps, TcParams &P, int num_sms, cudaStream_t stream); // yc_head_sm100_2cta.cu
+int launch_head_split(const yc_head_desc *d, int rows_total, const int *row_off, unsigned *left_mask, void *enc_fn, int num_sms,
+                      cudaStream_t stream);                                              // yc_head_sm100_split.cu
 
 int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, unsigned *left_mask,
                         const FusedDetect *fused, cudaStream_t stream)
@@ -327,12 +269,20 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     const int n_groups = d->na / na_tile;
     const int npad = round_up(na_tile * d->no, 16);
     const int npad_total = round_up(N, 16);
-    YC_REQUIRE(d->x_dtype == YC_BF16, YC_ERR_UNSUPPORTED, "tcgen05 head: feature maps must be bf16 (fp32 maps use the exact FFMA path)");
+    YC_REQUIRE(!(fused && d->x_dtype != YC_BF16), YC_ERR_UNSUPPORTED, "tcgen05 head: the fused step takes bf16 feature maps");
     YC_REQUIRE(!(fused && ibin), YC_ERR_UNSUPPORTED, "tcgen05 head: the fused step supports IDetect-style decode only");
-    YC_REQUIRE(npad <= TC_MAX_N && na_tile <= 3, YC_ERR_UNSUPPORTED,
-               "tcgen05 head: %d anchors x %d outputs do not fit the 256-column accumulator tile", d->na, d->no);
     EncodeTiledFn enc = encode_tiled();
     YC_REQUIRE(enc != nullptr, YC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (!g_num_sms) {
+        int dev = 0;
+        YC_CUDA(cudaGetDevice(&dev));
+        YC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (d->x_dtype == YC_F32)   // float32 maps: fp16 hi/lo split, three MMAs per k-step, float32-grade result
+        return launch_head_split(d, rows_total, row_off, left_mask, (void *)enc, g_num_sms - g_reserved_sms > 0 ? g_num_sms - g_reserved_sms : 1,
+                                 stream);
+    YC_REQUIRE(npad <= TC_MAX_N && na_tile <= 3, YC_ERR_UNSUPPORTED,
+               "tcgen05 head: %d anchors x %d outputs do not fit the 256-column accumulator tile", d->na, d->no);
 
     // per epilogue warp: z slab (32 rows) or, in the fused mode, the survivor queue (TC_QUEUE_ROWS x nc floats)
     const int no_out = ibin ? d->no - 2 * (d->bin_count + 1) + 2 : d->no;
@@ -451,11 +401,6 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     }
     P.total_tiles = tiles;
 
-    if (!g_num_sms) {
-        int dev = 0;
-        YC_CUDA(cudaGetDevice(&dev));
-        YC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
     if (pair) return launch_head_tc2(maps, P, g_num_sms - g_reserved_sms > 1 ? g_num_sms - g_reserved_sms : 2, stream);
     const int sms = g_num_sms - g_reserved_sms > 0 ? g_num_sms - g_reserved_sms : 1;
     const int grid = tiles < sms ? tiles : sms;

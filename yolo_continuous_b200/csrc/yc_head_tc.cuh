@@ -130,16 +130,35 @@ __device__ __forceinline__ void box_coord(const TcLevel &L, int bs, int j, int &
     p0 = (j - b * L.boxes_per_img) * 64;
 }
 
+// fp32-grade mode (yc_head_sm100_split.cu): a tile owns two accumulators, the main one (x_hi * w_hi) and, TC_SPLIT_CORR
+// columns further, the correction (x_hi * w_lo + x_lo * w_hi); the epilogue adds them in IEEE binary32.
+constexpr int TC_SPLIT_CORR = 128;
+
+// this thread's W accumulator values starting at `taddr` (SPLIT: main + correction)
+template <int W, bool SPLIT>
+__device__ __forceinline__ void ld_acc(uint32_t taddr, uint32_t *v)
+{
+    TmemLd<W>::ld(taddr, v);
+    if (SPLIT) {
+        uint32_t u[W];
+        TmemLd<W>::ld(taddr + (uint32_t)TC_SPLIT_CORR, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < W; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j])));
+    } else {
+        tmem_ld_wait();
+    }
+}
+
 // Epilogue for W consecutive accumulator columns [c0, c0+W) of this thread's row.
 //   RAW:   slab[o] = t                     (pre-sigmoid map, forward()'s list `x`)
 //   !RAW:  slab[o] = decode(sigmoid(t))    (z row; o<2 xy, o<4 wh: nets/idetect.py:40-42)
-template <int W, bool RAW>
+template <int W, bool RAW, bool SPLIT = false>
 __device__ __forceinline__ void epi_chunk(uint32_t taddr, int c0, const float2 *__restrict__ sb, float *__restrict__ srow,
                                           float gx, float gy, float stride, float stride_y, float aw, float ah)
 {
     uint32_t v[W];
-    TmemLd<W>::ld(taddr + (uint32_t)c0, v);
-    tmem_ld_wait();
+    ld_acc<W, SPLIT>(taddr + (uint32_t)c0, v);
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         const float2 s_b = __ldg(sb + c0 + j); // same address for the whole warp: one broadcast load
@@ -159,31 +178,30 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, int c0, const float2 *
     }
 }
 
-template <bool RAW>
+template <bool RAW, bool SPLIT = false>
 __device__ __forceinline__ void epi_row(uint32_t taddr, int no, const float2 *__restrict__ sb, float *__restrict__ srow,
                                         float gx, float gy, float stride, float stride_y, float aw, float ah)
 {
     int c0 = 0;
-    for (; c0 + 16 <= no; c0 += 16) epi_chunk<16, RAW>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah);
+    for (; c0 + 16 <= no; c0 += 16) epi_chunk<16, RAW, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah);
     const int rem = no - c0;
-    if (rem & 8) { epi_chunk<8, RAW>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); c0 += 8; }
-    if (rem & 4) { epi_chunk<4, RAW>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); c0 += 4; }
-    if (rem & 2) { epi_chunk<2, RAW>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); c0 += 2; }
-    if (rem & 1) { epi_chunk<1, RAW>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); }
+    if (rem & 8) { epi_chunk<8, RAW, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); c0 += 8; }
+    if (rem & 4) { epi_chunk<4, RAW, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); c0 += 4; }
+    if (rem & 2) { epi_chunk<2, RAW, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); c0 += 2; }
+    if (rem & 1) { epi_chunk<1, RAW, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, aw, ah); }
 }
 
 
 // IBin z row (reference nets/ibin.py:56-72, losses/sigmoid_bin.py:49-63) from the 127 accumulator columns of one
 // (pixel, anchor): [x, y | w: reg + bins | h: reg + bins | obj | cls] -> [x, y, w, h, obj, cls]; argmax over the
 // sigmoided bins takes the first maximum.  Same operation order as ibin_decode_kernel (generic path).
-template <int W>
+template <int W, bool SPLIT = false>
 __device__ __forceinline__ void ibin_chunk(uint32_t taddr, int c0, const float2 *__restrict__ sb, float *__restrict__ srow,
                                            float gx, float gy, float stride, float stride_y, int len, float &reg_w, float &reg_h, float &best_w,
                                            float &best_h, int &idx_w, int &idx_h)
 {
     uint32_t v[W];
-    TmemLd<W>::ld(taddr + (uint32_t)c0, v);
-    tmem_ld_wait();
+    ld_acc<W, SPLIT>(taddr + (uint32_t)c0, v);
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         const int o = c0 + j;
@@ -208,32 +226,35 @@ __device__ __forceinline__ void ibin_chunk(uint32_t taddr, int c0, const float2 
 }
 
 // sigmoid of the accumulator columns [cb, ce) (objectness / classes) into srow[o - shift]: no per-column case analysis
-template <int W>
+template <int W, bool SPLIT = false>
 __device__ __forceinline__ void sig_chunk(uint32_t taddr, int c0, const float2 *__restrict__ sb, float *__restrict__ srow, int shift)
 {
     uint32_t v[W];
-    TmemLd<W>::ld(taddr + (uint32_t)c0, v);
-    tmem_ld_wait();
+    ld_acc<W, SPLIT>(taddr + (uint32_t)c0, v);
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         const float2 s_b = __ldg(sb + c0 + j);
         srow[c0 + j - shift] = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
     }
 }
+// (SPLIT reads two accumulators per column: 16-column chunks keep the register count of the 32-column ones)
+template <bool SPLIT = false>
 __device__ __forceinline__ void epi_range_sig(uint32_t taddr, int cb, int ce, const float2 *__restrict__ sb, float *__restrict__ srow,
                                               int shift)
 {
+    constexpr int MW = SPLIT ? 16 : 32;
     int c0 = cb;
-    for (; c0 + 32 <= ce; c0 += 32) sig_chunk<32>(taddr, c0, sb, srow, shift);
+    for (; c0 + MW <= ce; c0 += MW) sig_chunk<MW, SPLIT>(taddr, c0, sb, srow, shift);
     const int rem = ce - c0;
-    if (rem & 16) { sig_chunk<16>(taddr, c0, sb, srow, shift); c0 += 16; }
-    if (rem & 8) { sig_chunk<8>(taddr, c0, sb, srow, shift); c0 += 8; }
-    if (rem & 4) { sig_chunk<4>(taddr, c0, sb, srow, shift); c0 += 4; }
-    if (rem & 2) { sig_chunk<2>(taddr, c0, sb, srow, shift); c0 += 2; }
-    if (rem & 1) { sig_chunk<1>(taddr, c0, sb, srow, shift); }
+    if (!SPLIT && (rem & 16)) { sig_chunk<16, SPLIT>(taddr, c0, sb, srow, shift); c0 += 16; }
+    if (rem & 8) { sig_chunk<8, SPLIT>(taddr, c0, sb, srow, shift); c0 += 8; }
+    if (rem & 4) { sig_chunk<4, SPLIT>(taddr, c0, sb, srow, shift); c0 += 4; }
+    if (rem & 2) { sig_chunk<2, SPLIT>(taddr, c0, sb, srow, shift); c0 += 2; }
+    if (rem & 1) { sig_chunk<1, SPLIT>(taddr, c0, sb, srow, shift); }
 }
 
 // columns [cb, ce) of the IBin row's box part; final_w / final_h: this range held all of the w / h block, finish it
+template <bool SPLIT = false>
 __device__ __forceinline__ void epi_range_ibin(uint32_t taddr, int cb, int ce, bool final_w, bool final_h, const float2 *__restrict__ sb,
                                                float *__restrict__ srow, float gx, float gy, float stride, float stride_y,
                                                float aw, float ah, const TcParams &P)
@@ -241,14 +262,15 @@ __device__ __forceinline__ void epi_range_ibin(uint32_t taddr, int cb, int ce, b
     const int len = P.bin_count + 1;
     float reg_w = 0.f, reg_h = 0.f, best_w = -1.f, best_h = -1.f;
     int idx_w = 0, idx_h = 0;
+    constexpr int MW = SPLIT ? 16 : 32;
     int c0 = cb;
-    for (; c0 + 32 <= ce; c0 += 32) ibin_chunk<32>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h);
+    for (; c0 + MW <= ce; c0 += MW) ibin_chunk<MW, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h);
     const int rem = ce - c0;
-    if (rem & 16) { ibin_chunk<16>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 16; }
-    if (rem & 8) { ibin_chunk<8>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 8; }
-    if (rem & 4) { ibin_chunk<4>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 4; }
-    if (rem & 2) { ibin_chunk<2>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 2; }
-    if (rem & 1) { ibin_chunk<1>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); }
+    if (!SPLIT && (rem & 16)) { ibin_chunk<16, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 16; }
+    if (rem & 8) { ibin_chunk<8, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 8; }
+    if (rem & 4) { ibin_chunk<4, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 4; }
+    if (rem & 2) { ibin_chunk<2, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); c0 += 2; }
+    if (rem & 1) { ibin_chunk<1, SPLIT>(taddr, c0, sb, srow, gx, gy, stride, stride_y, len, reg_w, reg_h, best_w, best_h, idx_w, idx_h); }
 #pragma unroll
     for (int d = 0; d < 2; ++d) {
         if (!(d == 0 ? final_w : final_h)) continue;
@@ -262,16 +284,18 @@ __device__ __forceinline__ void epi_range_ibin(uint32_t taddr, int cb, int ce, b
 }
 
 // raw columns [cb, ce) of this thread's row into the slab row
+template <bool SPLIT = false>
 __device__ __forceinline__ void epi_range_raw(uint32_t taddr, int cb, int ce, const float2 *__restrict__ sb, float *__restrict__ srow)
 {
+    constexpr int MW = SPLIT ? 16 : 32;
     int c0 = cb;
-    for (; c0 + 32 <= ce; c0 += 32) epi_chunk<32, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+    for (; c0 + MW <= ce; c0 += MW) epi_chunk<MW, true, SPLIT>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
     const int rem = ce - c0;
-    if (rem & 16) { epi_chunk<16, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 16; }
-    if (rem & 8) { epi_chunk<8, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 8; }
-    if (rem & 4) { epi_chunk<4, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 4; }
-    if (rem & 2) { epi_chunk<2, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 2; }
-    if (rem & 1) { epi_chunk<1, true>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); }
+    if (!SPLIT && (rem & 16)) { epi_chunk<16, true, SPLIT>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 16; }
+    if (rem & 8) { epi_chunk<8, true, SPLIT>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 8; }
+    if (rem & 4) { epi_chunk<4, true, SPLIT>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 4; }
+    if (rem & 2) { epi_chunk<2, true, SPLIT>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); c0 += 2; }
+    if (rem & 1) { epi_chunk<1, true, SPLIT>(taddr, c0, sb, srow, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f); }
 }
 
 
@@ -396,6 +420,86 @@ __device__ __forceinline__ void slab_store(float *__restrict__ gdst, const float
     } else { // unaligned span (odd shapes): plain coalesced stores
         for (int i = lane; i < nv * no; i += 32) gdst[i] = slab[i];
     }
+}
+
+
+// Non-fused epilogue of one epilogue warp for one tile: TMEM -> scale/bias -> sigmoid / decode (or raw, or IBin) -> slab in
+// shared memory -> bulk store of the warp's rows (one contiguous span of z / of the raw map).  `e` = epilogue warp index,
+// q = TMEM lane quadrant (warp % 4), g = anchor group of the tile, `tmem_tile` = first accumulator column of the tile's
+// buffer.  The buffer is handed back through `tempty` as soon as this warp's TMEM reads are done.
+// IBin (nets/ibin.py:56-72): 127 accumulator columns and as many sigmoids per row made the epilogue the bottleneck with
+// one warp per quadrant (1.28 ms against 0.30 ms with the epilogue switched off), so the three warps of a quadrant split
+// the columns [x y | w bins | h bins] [obj + a third of the classes] [rest] and fill ONE slab per quadrant, which the
+// first of them stores (named barriers 1..4 and 5..8, 96 threads each).
+template <bool SPLIT>
+__device__ __forceinline__ void store_epilogue(const TcParams &P, const TcLevel &L, int b, int p0, int g, int e, int q, int lane,
+                                               uint32_t tmem_tile, uint8_t *slabs, uint64_t *tempty)
+{
+    const int no = P.no, no_out = P.no_out;
+    const int a = P.ibin ? 0 : e >> 2;          // anchor of the tile handled by this warp (IBin: one anchor per tile)
+    const int prow0 = p0 + 32 * q;              // first pixel of this warp's 32 rows
+    const int nv = min(32, L.HW - prow0);       // valid rows (<= 0: nothing to store)
+    const int p = prow0 + lane;
+    const float gx = (float)(p % L.nx), gy = (float)(p / L.nx);
+    const int ar = g * P.na + a;                // anchor of the head this warp decodes
+    const float aw = L.anchor_wh[2 * ar], ah = L.anchor_wh[2 * ar + 1];
+    const float2 *sb = L.sb + ar * no;
+    const uint32_t taddr = tmem_tile + ((uint32_t)(32 * q) << 16) + (uint32_t)(a * no);
+    if (P.ibin) {
+        const int part = e >> 2;
+        const int len = P.bin_count + 1, s1 = 2 + 2 * len;       // s1: objectness column
+        const int sc = s1 + (no - s1) / 3;                       // classes are shared 1/3 : 2/3 by parts 1 and 2
+        float *zs = (float *)(slabs + (size_t)q * P.slab_bytes), *rs = zs + 32 * no_out;
+        if (part == 0) {
+            if (lane == 0) bulk_wait_read0();   // the previous stores from this quadrant's slab have been read out
+            __syncwarp();
+        }
+        named_bar_sync(1 + q, 96);
+        // part 0: [x y | w block]   part 1: [h block] + objectness and a third of the classes   part 2: the rest
+        const int cb = part == 0 ? 0 : (part == 1 ? 2 + len : sc), ce = part == 0 ? 2 + len : (part == 1 ? sc : no);
+        if (L.raw) epi_range_raw<SPLIT>(taddr, cb, ce, sb, rs + lane * no);
+        if (P.write_z) {
+            float *zrow = zs + lane * no_out;
+            if (part == 0) epi_range_ibin<SPLIT>(taddr, 0, 2 + len, true, false, sb, zrow, gx, gy, L.stride, L.stride_y, aw, ah, P);
+            if (part == 1) {
+                epi_range_ibin<SPLIT>(taddr, 2 + len, s1, false, true, sb, zrow, gx, gy, L.stride, L.stride_y, aw, ah, P);
+                epi_range_sig<SPLIT>(taddr, s1, sc, sb, zrow, 2 * len - 2);
+            }
+            if (part == 2) epi_range_sig<SPLIT>(taddr, sc, no, sb, zrow, 2 * len - 2);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
+        named_bar_sync(5 + q, 96);              // all three parts of the rows are in the slab
+        if (part == 0 && nv > 0) {
+            if (L.raw) slab_store(L.raw + (((size_t)b * P.na_real + ar) * L.HW + prow0) * no, rs, nv, no, lane);
+            if (P.write_z)
+                slab_store(P.z + ((size_t)b * P.rows_total + L.row_off + (size_t)ar * L.HW + prow0) * no_out, zs, nv,
+                           no_out, lane);
+        }
+        return;
+    }
+    float *slab = (float *)(slabs + (size_t)e * P.slab_bytes);
+    if (L.raw) {
+        if (lane == 0) bulk_wait_read0(); // previous store from this slab has been read out
+        __syncwarp();
+        epi_row<true, SPLIT>(taddr, no, sb, slab + lane * no, gx, gy, L.stride, L.stride_y, aw, ah);
+        if (nv > 0)
+            slab_store(L.raw + (((size_t)b * P.na_real + ar) * L.HW + prow0) * no, slab, nv, no, lane);
+    }
+    if (P.write_z) {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        epi_row<false, SPLIT>(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, L.stride_y, aw, ah);
+    }
+    // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty);
+    if (P.write_z && nv > 0)
+        slab_store(P.z + ((size_t)b * P.rows_total + L.row_off + (size_t)ar * L.HW + prow0) * no_out, slab, nv,
+                   no_out, lane);
 }
 
 

@@ -279,10 +279,16 @@ class PostBackbone:
             prev = self.cur if self._in_flight else None
             self.cur ^= 1
             c = self.cur
-            # The first step of a stream of batches has no previous batch: its graph carries the head kernel only, so
-            # that results an earlier eager run_device() call left in the other output buffer stay untouched
-            with_tail = self._in_flight
-            key = tuple(x.data_ptr() for x in features) + (c, with_tail)
+            # The first step of a stream of batches has no previous batch: the head kernel alone is launched (eagerly, one
+            # call), so that results an earlier eager run_device() call left in the other output buffer stay untouched
+            if not self._in_flight:
+                for i, x in enumerate(features):
+                    if x.dtype != self.dtype or tuple(x.shape) != tuple(self.x_dev[i].shape) or not x.is_contiguous():
+                        raise _lib.YcError(f"level {i}: expected contiguous {tuple(self.x_dev[i].shape)} {self.dtype}")
+                self._pipelined_step(features, c, with_tail=False)
+                self._in_flight = True
+                return None
+            key = tuple(x.data_ptr() for x in features) + (c,)
             g = self._pgraphs.get(key)
             if g is None:
                 for i, x in enumerate(features):
@@ -293,7 +299,7 @@ class PostBackbone:
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
-                    self._pipelined_step(features, c, with_tail)
+                    self._pipelined_step(features, c)
                 if len(self._pgraphs) > 16:
                     self._pgraphs.clear()
                 self._pgraphs[key] = g
