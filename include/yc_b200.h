@@ -66,15 +66,16 @@ YC_API int yc_device_check(int dev);
  * (b' = b + W.ia, binary64 accumulation), ImplicitM stays a per-channel epilogue scale.
  * yc_head_pack writes one blob per level:
  *   [bias2 f32 Npad][scale f32 Npad][scale_split f32 Npad][(scale,bias2) f32x2 Npad][(scale_split,bias2) f32x2 Npad]
- *   [w32 f32 N*K][w_hi_t f16 K*Npad][w_lo_t f16 K*Npad][w_bf16 Npad*K]          (Npad = N rounded up to 16)
+ *   [w32 f32 N*K][w_hi_t f16 K*(na*npad_g)][w_lo_t likewise][w_bf16 Npad*K]   (Npad = N rounded up to 16, npad_g = N/na
+ *   rounded up to 16: in the transposed copies the channels of anchor a start at column a*npad_g)
  * w_hi_t + w_lo_t = W[c,:] * 2^shift(c), split into two fp16 numbers and stored transposed: the operands of the
  * float32-grade tensor-core path (three fp16 MMAs per k-step, see csrc/yc_head_sm100_split.cu); scale_split undoes the
  * row scaling and the activation scaling.
  * W [N,K] f32 row-major (Conv2d weight [N,K,1,1]); bias [N] or NULL; ia [K] or NULL; im [N] or NULL.
  */
 YC_API size_t yc_head_pack_bytes(int N, int K);
-YC_API int yc_head_pack(const float *W, const float *bias, const float *ia, const float *im, int N, int K,
-                 void *blob, yc_stream_t stream);
+YC_API int yc_head_pack(const float *W, const float *bias, const float *ia, const float *im, int N, int K, int na,
+                 void *blob, yc_stream_t stream);   /* na = anchors per level (row c of W = anchor c / (N/na)) */
 
 typedef struct yc_head_level {
     const void *x;     /* [bs, K, H, W] NCHW feature map, dtype = yc_head_desc.x_dtype */

@@ -55,7 +55,7 @@ def _load():
     lib.yc_device_check.argtypes = [C.c_int]
     lib.yc_head_pack_bytes.restype = C.c_size_t
     lib.yc_head_pack_bytes.argtypes = [C.c_int, C.c_int]
-    lib.yc_head_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+    lib.yc_head_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p]
     lib.yc_head_forward.argtypes = [C.POINTER(HeadDesc), C.c_void_p]
     lib.yc_decode_box.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

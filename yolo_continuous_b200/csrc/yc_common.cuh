@@ -45,8 +45,9 @@ struct BlobView {
     const float2 *sb;         // (scale, bias2) interleaved: one 8-byte broadcast load per column in the epilogue
     const float2 *sb_split;   // (scale_split, bias2)
     const float *w32;         // [N,K]
-    const __half *w_hi_t;     // [K,Npad]  fp16(W * 2^shift(c)), transposed (MN-major B operand)
-    const __half *w_lo_t;     // [K,Npad]  fp16(W * 2^shift(c) - w_hi)
+    const __half *w_hi_t;     // [K, na*npad_g]  fp16(W * 2^shift(c)), transposed (MN-major B operand); anchor a's `no` channels
+                              //   start at column a*npad_g, npad_g = round_up(no, 16): TMA box starts must be 16-byte aligned
+    const __half *w_lo_t;     // [K, na*npad_g]  fp16(W * 2^shift(c) - w_hi)
     const __nv_bfloat16 *w_bf; // [Npad,K]
 };
 
@@ -67,8 +68,10 @@ __host__ __device__ inline BlobView blob_view(const void *blob, int N, int K)
     v.w32 = (const float *)p;                    p += w32b;
     size_t w16b = sizeof(__half) * (size_t)Npad * K;
     w16b = (w16b + 127) / 128 * 128;
-    v.w_hi_t = (const __half *)p;                p += w16b;
-    v.w_lo_t = (const __half *)p;                p += w16b;
+    size_t wtb = sizeof(__half) * (size_t)(Npad + 16 * YC_MAX_ANCHORS) * K;   // room for any per-anchor padding
+    wtb = (wtb + 127) / 128 * 128;
+    v.w_hi_t = (const __half *)p;                p += wtb;
+    v.w_lo_t = (const __half *)p;                p += wtb;
     v.w_bf = (const __nv_bfloat16 *)p;
     return v;
 }

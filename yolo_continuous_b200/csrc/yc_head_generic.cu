@@ -16,17 +16,13 @@ namespace yc {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) head_pack_kernel(const float *__restrict__ W, const float *__restrict__ bias,
                                                         const float *__restrict__ ia, const float *__restrict__ im, int N,
-                                                        int K, int Npad, float *bias2, float *scale, float *scale_split,
+                                                        int K, int Npad, int no, int npad_g, int wt, float *bias2, float *scale, float *scale_split,
                                                         float2 *sb, float2 *sb_split, float *w32, __half *w_hi, __half *w_lo, __nv_bfloat16 *w_bf)
 {
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= Npad) return;
     if (c >= N) { // zero padding rows: the MMA sees zeros, the epilogue never reads them
-        for (int k = lane; k < K; k += 32) {
-            w_hi[(size_t)k * Npad + c] = __float2half_rn(0.f);
-            w_lo[(size_t)k * Npad + c] = __float2half_rn(0.f);
-            w_bf[(size_t)c * K + k] = __float2bfloat16_rn(0.f);
-        }
+        for (int k = lane; k < K; k += 32) w_bf[(size_t)c * K + k] = __float2bfloat16_rn(0.f);
         if (lane == 0) {
             bias2[c] = 0.f; scale[c] = 0.f; scale_split[c] = 0.f;
             sb[c] = make_float2(0.f, 0.f); sb_split[c] = make_float2(0.f, 0.f);
@@ -52,13 +48,14 @@ __global__ void __launch_bounds__(128) head_pack_kernel(const float *__restrict_
     if (amax > 0.f && isfinite(amax)) shift = 12 - ilogbf(amax);
     shift = max(-60, min(60, shift));
     const float up = ldexpf(1.0f, shift);
+    const int tcol = (c / no) * npad_g + c % no;   // column of channel c in the per-anchor padded transposed copies
     for (int k = lane; k < K; k += 32) {
         const float w = wr[k];
         const float ws = w * up; // exact (power of two)
         const __half hi = __float2half_rn(ws);
         const __half lo = __float2half_rn(ws - __half2float(hi));
-        w_hi[(size_t)k * Npad + c] = hi;   // transposed: the split kernel reads the weights as an MN-major operand
-        w_lo[(size_t)k * Npad + c] = lo;
+        w_hi[(size_t)k * wt + tcol] = hi;   // transposed: the split kernel reads the weights as an MN-major operand
+        w_lo[(size_t)k * wt + tcol] = lo;
         w_bf[(size_t)c * K + k] = __float2bfloat16_rn(w);
         w32[(size_t)c * K + k] = w;
     }
@@ -319,18 +316,23 @@ extern "C" size_t yc_head_pack_bytes(int N, int K)
     const int Npad = round_up(N, 16);
     size_t w32b = round_up_sz(sizeof(float) * (size_t)N * K, 128);
     size_t w16b = round_up_sz(sizeof(__half) * (size_t)Npad * K, 128);
-    return sizeof(float) * 7 * (size_t)Npad + w32b + 3 * w16b + 256;
+    size_t wtb = round_up_sz(sizeof(__half) * (size_t)(Npad + 16 * YC_MAX_ANCHORS) * K, 128);
+    return sizeof(float) * 7 * (size_t)Npad + w32b + w16b + 2 * wtb + 256;
 }
 
-extern "C" int yc_head_pack(const float *W, const float *bias, const float *ia, const float *im, int N, int K, void *blob,
-                            yc_stream_t stream)
+extern "C" int yc_head_pack(const float *W, const float *bias, const float *ia, const float *im, int N, int K, int na,
+                            void *blob, yc_stream_t stream)
 {
     YC_REQUIRE(W && blob && N > 0 && K > 0, YC_ERR_INVALID, "yc_head_pack: bad argument");
+    YC_REQUIRE(na >= 1 && na <= YC_MAX_ANCHORS && N % na == 0, YC_ERR_INVALID, "yc_head_pack: N = %d is not %d anchors x no", N, na);
     YC_REQUIRE(((uintptr_t)blob & 127) == 0, YC_ERR_INVALID, "yc_head_pack: blob must be 128-byte aligned");
     const int Npad = round_up(N, 16);
+    const int no = N / na, npad_g = round_up(no, 16), wt = na * npad_g;
     BlobView v = blob_view(blob, N, K);
+    // padding columns of the transposed copies feed accumulator columns nobody reads, but must not hold NaN patterns
+    YC_CUDA(cudaMemsetAsync((void *)v.w_hi_t, 0, (size_t)((const char *)v.w_bf - (const char *)v.w_hi_t), (cudaStream_t)stream));
     head_pack_kernel<<<(Npad + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
-        W, bias, ia, im, N, K, Npad, (float *)v.bias2, (float *)v.scale, (float *)v.scale_split, (float2 *)v.sb, (float2 *)v.sb_split,
+        W, bias, ia, im, N, K, Npad, no, npad_g, wt, (float *)v.bias2, (float *)v.scale, (float *)v.scale_split, (float2 *)v.sb, (float2 *)v.sb_split,
         (float *)v.w32,
         (__half *)v.w_hi_t, (__half *)v.w_lo_t, (__nv_bfloat16 *)v.w_bf);
     YC_CUDA(cudaGetLastError());

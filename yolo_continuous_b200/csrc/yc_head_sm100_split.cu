@@ -107,19 +107,25 @@ head_tcs_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
             const TileCoord tc = coord(t);
             const int nkb = (P.lv[tc.lv].K + TS_BK - 1) / TS_BK;
             const CUtensorMap *ma = &maps.a[tc.lv], *mh = &maps.b[2 * tc.lv], *ml = &maps.b[2 * tc.lv + 1];
-            const int n0 = tc.g * P.no;    // first weight column of this anchor
+            const int n0 = tc.g * P.npad_g;   // first weight column of this anchor in the padded transposed copies
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 if (elect_one()) {
                     uint8_t *sa = stage_base + stage * TS_STAGE_BYTES, *sb = sa + TS_A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], tx);
+                    const bool da = !(P.debug & 16), db = !(P.debug & 32);
+                    if (da || db) mbar_arrive_expect_tx(&full_bar[stage], (da ? (uint32_t)TS_A_BYTES : 0u) + (db ? 4u * P.b_box_bytes : 0u));
+                    else mbar_arrive(&full_bar[stage]);
+                    if (da) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)   // four {32 px, 32 k} float32 boxes
                         tma_load_3d(sa + j * 4096, ma, &full_bar[stage], tc.p0 + 32 * j, kb * TS_BK, tc.b);
+                    }
+                    if (db) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) { // {64 n, 32 k} boxes of w_hi and w_lo
                         tma_load_2d(sb + j * 4096, mh, &full_bar[stage], n0 + 64 * j, kb * TS_BK);
                         tma_load_2d(sb + TS_B_HALF + j * 4096, ml, &full_bar[stage], n0 + 64 * j, kb * TS_BK);
+                    }
                     }
                 }
                 __syncwarp();
@@ -153,6 +159,7 @@ head_tcs_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                     const uint64_t so = (uint64_t)((uint32_t)(stage * TS_STAGE_BYTES) >> 4);
 #pragma unroll
                     for (int k = 0; k < TS_BK / 16; ++k) {
+                        if (P.debug & 2) break;
                         const uint64_t ko = so + (uint64_t)((k * 2048) >> 4);
                         const uint32_t acc = (uint32_t)((kb | k) != 0);
                         mma_f16(t_corr, d_xlo + ko, d_whi + ko, idesc, acc);
@@ -182,6 +189,12 @@ head_tcs_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
             for (int kb = 0; kb < nkb; ++kb) {
                 uint8_t *sa = stage_base + stage * TS_STAGE_BYTES;
                 mbar_wait(&full_bar[stage], phase);
+                if (P.debug & 64) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&conv_bar[stage]);
+                    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+                    continue;
+                }
                 float4 v[8];
                 const uint8_t *src = sa + pq * 4096 + k * 128;
 #pragma unroll
@@ -219,6 +232,12 @@ head_tcs_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
             const int buf = it & 1;
             mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
+            if (P.debug & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                continue;
+            }
             store_epilogue<true>(P, P.lv[tc.lv], tc.b, tc.p0, tc.g, e, q, lane, tmem_base + (uint32_t)(buf * TC_MAX_N), slabs,
                                  &tempty_bar[buf]);
         }
@@ -242,7 +261,10 @@ int launch_head_split(const yc_head_desc *d, int rows_total, const int *row_off,
     EncodeTiledFn enc = (EncodeTiledFn)enc_fn;
     const int N = d->na * d->no;
     const bool ibin = d->kind == YC_HEAD_IBIN;
-    const int npad = round_up(d->no, 16), npad_total = round_up(N, 16);
+    int dbg = 0;
+    { const char *e = getenv("YC_TS_DEBUG"); dbg = e ? atoi(e) : 0; }
+    const int npad_g = round_up(d->no, 16), wt = d->na * npad_g;   // layout of w_hi_t / w_lo_t (yc_head_pack)
+    const int npad = (dbg & 8) ? 128 : npad_g;
     YC_REQUIRE(npad <= TC_SPLIT_CORR, YC_ERR_UNSUPPORTED, "tcgen05 fp32 head: %d outputs per anchor do not fit 128 accumulator columns",
                d->no);
     const int no_out = ibin ? d->no - 2 * (d->bin_count + 1) + 2 : d->no;
@@ -282,6 +304,7 @@ int launch_head_split(const yc_head_desc *d, int rows_total, const int *row_off,
     P.epi_warps = epi_warps;
     P.na_real = d->na; P.no_out = no_out;
     P.rows_total = rows_total;
+    P.npad_g = npad_g;
     P.write_z = d->kind != YC_HEAD_RAW ? 1 : 0;
     if (ibin) {
         P.ibin = 1; P.bin_count = d->bin_count;
@@ -293,6 +316,7 @@ int launch_head_split(const yc_head_desc *d, int rows_total, const int *row_off,
     P.b_box_bytes = 64 * TS_BK * 2;    // one {64 n, 32 k} fp16 box
     P.slab_bytes = slab_bytes;
     P.stages = stages;
+    P.debug = dbg;
     int tiles = 0;
     for (int s = 0; s < n; ++s) {
         const int i = order[s];
@@ -320,9 +344,9 @@ int launch_head_split(const yc_head_desc *d, int rows_total, const int *row_off,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             YC_REQUIRE(r == CUDA_SUCCESS, YC_ERR_CUDA, "cuTensorMapEncodeTiled(A f32, level %d) failed: %d", i, (int)r);
         }
-        for (int h = 0; h < 2; ++h) {   // B: w_hi_t / w_lo_t [K, Npad_total] fp16 (weights transposed), box {64 n, 32 k}
-            cuuint64_t gdim[2] = {(cuuint64_t)npad_total, (cuuint64_t)lv.K};
-            cuuint64_t gstr[1] = {(cuuint64_t)npad_total * 2};
+        for (int h = 0; h < 2; ++h) {   // B: w_hi_t / w_lo_t [K, na*npad_g] fp16 (weights transposed, per-anchor padded), box {64 n, 32 k}
+            cuuint64_t gdim[2] = {(cuuint64_t)wt, (cuuint64_t)lv.K};
+            cuuint64_t gstr[1] = {(cuuint64_t)wt * 2};
             cuuint32_t box[2] = {64, (cuuint32_t)TS_BK}, est[2] = {1, 1};
             CUresult r = enc(&maps.b[2 * s + h], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)(h ? bv.w_lo_t : bv.w_hi_t), gdim,
                              gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

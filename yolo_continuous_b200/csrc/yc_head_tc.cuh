@@ -56,6 +56,7 @@ struct TcParams {
     int n_lv;
     int total_tiles;
     int bs, na, no, npad;      // na = anchors per MMA tile, no = accumulator columns per anchor
+    int npad_g;                // split kernel: columns per anchor in the transposed weight copies (round_up(no, 16))
     int epi_warps;             // epilogue warps: 4 per anchor of the tile; IBin (one anchor per tile, 127 sigmoids per row):
                                // 12 = 3 per TMEM lane quadrant, each taking a third of the columns
     int na_real;               // anchors of the head (raw map indexing)

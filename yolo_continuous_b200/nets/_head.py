@@ -73,7 +73,7 @@ class HeadBase(nn.Module):
         _lib.check(_lib.lib.yc_head_pack(w.data_ptr(), b.data_ptr() if b is not None else None,
                                          a_.data_ptr() if a_ is not None else None,
                                          m_.data_ptr() if m_ is not None else None,
-                                         n, k, blob.data_ptr(), _lib.stream_ptr(device)), "yc_head_pack")
+                                         n, k, self.na, blob.data_ptr(), _lib.stream_ptr(device)), "yc_head_pack")
         self._packed[tag] = (key, blob)
         return blob
 

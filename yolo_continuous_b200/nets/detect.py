@@ -26,6 +26,7 @@ class Detect(nn.Module):
         self.len_output = num_classes + 5
         self.num_layers = len(anchors)
         self.num_anchors_each_layer = len(anchors[0]) // 2
+        self.na = self.num_anchors_each_layer   # read by the shared parameter packing (HeadBase._blob)
         n = self.num_anchors_each_layer * self.len_output
         self.yolo_head_P3 = nn.Conv2d(ch[0], n, 1)
         self.yolo_head_P4 = nn.Conv2d(ch[1], n, 1)
