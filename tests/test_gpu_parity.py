@@ -843,8 +843,12 @@ def test_fused_pair_kernel_vs_oracle_c2_shapes():
     scale = box_scale(p["anchors"], [8.0, 16.0, 32.0], C2_SHAPES, head.na, 85)
     assert_close_scaled(z.cpu().numpy(), z_ref, scale, RTOL_BF16, "tcgen05 forward @ C2 shapes")
     assert_close_scaled(z.cpu().numpy(), z_ref, scale, 1e-4, "tcgen05 forward @ C2 shapes (tight)")
-    for i in range(3):   # class logits reach |t| ~ 10: the accumulation noise is relative
-        np.testing.assert_allclose(raws[i].cpu().numpy(), raw_ref[i], rtol=1e-4, atol=1e-4)
+    for i in range(3):
+        # raw logits at the bf16 tolerance |a-b| <= 1e-3 * max(|ref|, 1).  (The oracle multiplies the bf16-rounded
+        # weights with x + ia; the product folds ia into the bias with the float32 weights: with the large class-row
+        # weights of this head the two differ by up to ~2e-4 on a logit, far above the accumulation noise.)
+        r, want_r = raws[i].cpu().numpy(), raw_ref[i]
+        assert np.all(np.abs(r - want_r) <= RTOL_BF16 * np.maximum(np.abs(want_r), 1.0)), float(np.abs(r - want_r).max())
     # (2) fused step: CTA-pair kernel (default) and the 1-CTA kernel (YC_TC_2CTA=0), eager and pipelined graphs
     import os
     for two_cta in ("1", "0"):
