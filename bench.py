@@ -465,7 +465,21 @@ def main():
     # one collective per GATHER_EVERY steps (see DetectionGather): 16 steps = 1024 images per rank per exchange
     # (the host side of a NCCL call costs 0.2-0.6 ms at 2-8 ranks: one per step would make the loop host-bound)
     GATHER_EVERY = int(os.environ.get("YC_GATHER_EVERY", "16"))
-    gather = DetectionGather(pipe.message(GATHER_ROWS).numel(), dev, every=GATHER_EVERY) if world > 1 else None
+    # Exchange of the detections (world > 1).  Default: the repo's own kernels over NVLink peer memory (PeerExchange: one
+    # push kernel + one wait kernel per step inside the step's CUDA graph, no NCCL call and no host work per step);
+    # YC_EXCHANGE=nccl (or a box without CUDA IPC peer access) selects the grouped NCCL all-gather.
+    gather, xchg = None, None
+    if world > 1:
+        if os.environ.get("YC_EXCHANGE", "peer") == "peer" and overlap:
+            try:
+                from yolo_continuous_b200.parallel import PeerExchange
+                xchg = PeerExchange(pipe.hdr_ints, args.bs, GATHER_ROWS, dev)
+                pipe.attach_exchange(xchg)
+            except _lib.YcError as e:   # every rank fails or succeeds alike (same box, same driver)
+                print(f"[bench] peer exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+                xchg = None
+        if xchg is None:
+            gather = DetectionGather(pipe.message(GATHER_ROWS).numel(), dev, every=GATHER_EVERY)
     xs = make_maps(args.bs, 1234 + rank, tdt, dev)
     for d_, h_ in zip(xs, pipe.x_host):
         h_.copy_(d_)
@@ -481,21 +495,24 @@ def main():
 
     def step():
         if pipelined:
-            prev = pipe.submit(xs)
-            if world > 1 and prev is not None:
+            prev = pipe.submit(xs)           # with the peer exchange attached the graph also pushes / awaits the messages
+            if gather is not None and prev is not None:
                 gather.gather_async(pipe.message(GATHER_ROWS, previous=True))
         else:
             pipe.run_device(xs)
-            if world > 1:
+            if gather is not None:
                 gather.gather_async(pipe.message(GATHER_ROWS), stream=pipe.tail_stream)
 
     def finish():
         slot = None
         if pipelined:
             pipe.drain()
-            if world > 1:
+            if gather is not None:
                 slot = gather.gather_async(pipe.message(GATHER_ROWS))
-        if world > 1:
+        if xchg is not None:
+            pipe.wait()
+            xchg.wait()                      # the last step's messages of all ranks have arrived
+        if gather is not None:
             s2 = gather.flush()
             slot = s2 if s2 is not None else slot
             gather.wait()
@@ -518,18 +535,24 @@ def main():
         # this rank's latest message(s): its own slot must be bit-identical to its local result, and every rank's
         # header must agree with a plain all-gather of the local counts.
         torch.cuda.synchronize()
-        n_in_group = (W - 1) % GATHER_EVERY + 1
-        got = gather.unpack(slot, args.bs, pipe.hdr_ints, GATHER_ROWS, n=n_in_group)
         rows_l, _, counts_l, offs_l = pipe._views(pipe.cur)
         total_l = int(offs_l[-1])
-        last = got[rank][-1] if GATHER_EVERY > 1 else got[rank]
+        if xchg is not None:
+            sp, sw, err = xchg.state()
+            assert err == 0 and sp == sw == W, f"peer exchange state {(sp, sw, err)} after {W} steps"
+            got = xchg.unpack(sw - 1)
+            last = got[rank]
+        else:
+            n_in_group = (W - 1) % GATHER_EVERY + 1
+            got = gather.unpack(slot, args.bs, pipe.hdr_ints, GATHER_ROWS, n=n_in_group)
+            got = [g_[-1] if GATHER_EVERY > 1 else g_ for g_ in got]
+            last = got[rank]
         ok = torch.equal(last[0], counts_l) and int(last[1]) == total_l and \
             torch.equal(last[2][:min(total_l, GATHER_ROWS)], rows_l[:min(total_l, GATHER_ROWS)])
         all_counts = [torch.empty_like(counts_l) for _ in range(world)]
         dist.all_gather(all_counts, counts_l.contiguous())
         for r in range(world):
-            gl = got[r][-1] if GATHER_EVERY > 1 else got[r]
-            ok = ok and torch.equal(gl[0], all_counts[r])
+            ok = ok and torch.equal(got[r][0], all_counts[r])
         assert ok, "detection exchange: gathered messages differ from what the ranks produced"
         exchange_check = "gathered == produced (own rows bit-identical; all ranks' counts vs a plain all-gather)"
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -636,11 +659,13 @@ def main():
     for _ in range(K):
         o = host_step()
         out = o if o is not None else out
-        if world > 1:
+        if gather is not None:
             gather.gather_async(pipe.message(GATHER_ROWS), stream=pipe.tail_stream)
     if overlap:
         out = pipe.drain_host()
-    if world > 1:
+    if xchg is not None:
+        xchg.wait(pipe.tail_stream)
+    if gather is not None:
         gather.flush()
         gather.wait()
     torch.cuda.synchronize()
@@ -671,6 +696,11 @@ def main():
     h2d_ceiling_ips = world * n_copy * args.bs / c_s
 
     nms_lat = nms_latency(head, xs, dev, tdt) if rank == 0 and not args.no_extras else None
+    if xchg is not None:
+        sp, sw, err = xchg.state()
+        assert err == 0 and sp == sw, f"peer exchange state {(sp, sw, err)} at the end of the run"
+        pipe.attach_exchange(None)
+        xchg.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -724,9 +754,13 @@ def main():
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
         "config": dict(workload_config(args.bs, args.dtype), pipelining=pipelining_note(overlap),
-                       **({"exchange": f"one NCCL all-gather per {GATHER_EVERY} steps: per rank and step the header + the first "
-                                       f"{GATHER_ROWS} detection rows; every step's detections reach every rank inside the "
-                                       f"timed region", "exchange_check": exchange_check} if world > 1 else {})),
+                       **({"exchange": (f"own kernels over NVLink peer memory (CUDA IPC): per step one push kernel stores the header + "
+                                        f"the first {GATHER_ROWS} detection rows into every rank's receive buffer and raises a "
+                                        f"flag, one wait kernel awaits the previous step's flags -- both inside the step's CUDA "
+                                        f"graph, no NCCL call, no host work" if xchg is not None else
+                                        f"one NCCL all-gather per {GATHER_EVERY} steps: per rank and step the header + the first "
+                                        f"{GATHER_ROWS} detection rows") + "; every step's detections reach every rank inside "
+                                       "the timed region", "exchange_check": exchange_check} if world > 1 else {})),
         "clocks": clocks,
         "sustained": sustained,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
@@ -735,7 +769,7 @@ def main():
                                 "frac": e2e_value / h2d_ceiling_ips,
                                 "what": f"plain pinned cudaMemcpyAsync of the same {pipe.h2d_bytes()} bytes per step on all "
                                         f"{world} rank(s) at once, no kernels"}},
-        "gpu_launches": K * pipe.kernels_per_step,
+        "gpu_launches": K * (pipe.kernels_per_step + (2 if xchg is not None else 0)),
         "roofline": roofline,
         "detections_per_step": n_det, "nms_latency_bs1": nms_lat,
     }

@@ -170,6 +170,35 @@ YC_API int yc_nms_workspace_reset(const yc_nms_params *p, void *workspace, size_
 YC_API int yc_detect_fused_head_noreset(const yc_head_desc *desc, const yc_nms_params *p, void *workspace,
                                  size_t workspace_bytes, yc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Detection exchange between the GPUs of one box (images shard across ranks, the only exchange is
+ * the gather of the variable-length detection lists; the reference has no counterpart).  No collective library and no
+ * host work per step: yc_xchg_push launches a kernel that stores this rank's message (the [counts | offsets] header and
+ * the first rows of the detection list, exactly the buffer prefix yc_detect_fused leaves) into a slot of EVERY rank's
+ * receive buffer over NVLink peer mappings and raises a flag there; yc_xchg_wait launches a kernel that waits until the
+ * messages of all ranks with this rank's next sequence number have arrived.  Sequence numbers live on the device: both
+ * launches can be captured in a CUDA graph and replayed.  Credits: a slot is reused only after the receiver has waited
+ * for a later message (calling wait for sequence number j declares everything before j consumed).
+ * Set-up: every rank calls yc_xchg_alloc (cudaMalloc + IPC handle), the 64-byte handles are exchanged by the host
+ * (any transport), every rank opens the others' with yc_xchg_open and uploads the `world` base pointers (its own buffer at
+ * index `rank`) as a device array `peers_dev`.
+ * Receive buffer: message of rank r with sequence number q at  buf + ((q % slots) * world + r) * msg_bytes.
+ */
+YC_API size_t yc_xchg_bytes(int world, int slots, size_t msg_bytes);
+YC_API int yc_xchg_alloc(int world, int slots, size_t msg_bytes, void **buf, uint8_t *handle64);
+YC_API int yc_xchg_open(const uint8_t *handle64, void **peer_buf);
+YC_API int yc_xchg_close(void *peer_buf);
+YC_API int yc_xchg_free(void *buf);
+/* msg: device [hdr_ints int32 (counts bs | offsets bs+1 | pad to a multiple of 4)][rows x 7 f32]; at most max_rows rows move. */
+YC_API int yc_xchg_push(const void *msg, int hdr_ints, int bs, int max_rows, void *const *peers_dev, int world, int rank,
+                 int slots, size_t msg_bytes, yc_stream_t stream);
+/* lag: the kernel returns at once unless this rank has itself pushed message (next wait sequence number + lag) already;
+ * "push(i); wait(lag = 1)" per step waits for step i - 1 and never spins in the steady state; lag = 0 waits for the latest. */
+YC_API int yc_xchg_wait(void *const *peers_dev, int world, int rank, int slots, size_t msg_bytes, int lag, yc_stream_t stream);
+/* out4 (host): next push sequence number, next wait sequence number, internal, error (1 = a wait timed out). Synchronises. */
+YC_API int yc_xchg_state(const void *buf, int world, int slots, size_t msg_bytes, uint32_t *out4, yc_stream_t stream);
+
+
 /* torchvision.ops.nms drop-in for one box set (detect.py:133): boxes [n,4] xyxy, scores [n].
  * keep [n] receives kept indices in score order, *keep_count_dev their number. workspace from
  * yc_nms_workspace_bytes(1, n, 1). */

@@ -74,9 +74,34 @@ def main():
                         for q in range(world):
                             assert torch.equal(all_counts[q], local_res[(q, 4)][0])
                             assert torch.equal(all_rows[q], local_res[(q, 4)][1])
+    # ---- the repo's own exchange: push / wait kernels over NVLink peer memory, inside the per-step graphs ------------
+    from yolo_continuous_b200.parallel import PeerExchange
+    for gather_rows in (4096, 8):
+        xc = PeerExchange(pipe.hdr_ints, bs, gather_rows, dev, slots=4)
+        pipe.attach_exchange(xc)
+        n_rounds = 3                   # 15 messages: every slot is reused three times (credits / acknowledgements)
+        for rnd in range(n_rounds):
+            for s in range(n_steps):
+                pipe.submit(inputs(rank, s))
+                if rank == 1 and s == 2:
+                    torch.cuda._sleep(20_000_000)    # one rank falls behind: the others must wait, not overwrite
+        pipe.drain()
+        xc.wait()
+        sp, sw, err = xc.state()
+        assert (sp, sw, err) == (n_rounds * n_steps, n_rounds * n_steps, 0), (sp, sw, err)
+        # the last `slots` messages are still in the receive buffer: sequence number q holds step q % n_steps
+        for q in range(sp - 3, sp):
+            for r, (counts, total, rows) in enumerate(xc.unpack(q)):
+                want_c, want_r = local_res[(r, q % n_steps)]
+                assert torch.equal(counts, want_c), ("peer", gather_rows, r, q)
+                assert int(total) == want_r.shape[0]
+                m = min(int(total), gather_rows)
+                assert torch.equal(rows[:m], want_r[:m]), ("peer", gather_rows, r, q)
+        pipe.attach_exchange(None)
+        xc.close()
     dist.barrier()
     if rank == 0:
-        print("NCCL_GATHER_OK world", world)
+        print("NCCL_GATHER_OK PEER_EXCHANGE_OK world", world)
     dist.destroy_process_group()
 
 

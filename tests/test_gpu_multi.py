@@ -25,7 +25,8 @@ def _torchrun(script, n, timeout=600):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_detection_gather_over_nccl_two_ranks():
-    """DetectionGather / gather_detections over NCCL return, on every rank, bit-identical rows and counts to what each
-    rank produced, including ranks whose detections overflow the fixed-size message."""
+    """DetectionGather / gather_detections over NCCL and PeerExchange (the repo's own push / wait kernels over NVLink peer
+    memory) return, on every rank, bit-identical rows and counts to what each rank produced, including ranks whose
+    detections overflow the fixed-size message, slot reuse and a rank that falls behind."""
     r = _torchrun("mp_gather_worker.py", 2)
-    assert r.returncode == 0 and "NCCL_GATHER_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "NCCL_GATHER_OK PEER_EXCHANGE_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -41,7 +41,9 @@ EXPORTS = ["yc_last_error", "yc_version", "yc_device_check", "yc_head_pack_bytes
            "yc_head_forward", "yc_decode_box", "yc_nms_workspace_bytes", "yc_nms_batched",
            "yc_nms_single", "yc_box_iou", "yc_cvt_bbox", "yc_detect_fused",
            "yc_detect_fused_head", "yc_nms_from_candidates", "yc_nms_workspace_reset", "yc_detect_fused_head_noreset",
-           "yc_letterbox_batch", "yc_format_detections", "yc_reserve_sms", "yc_copy_async"]
+           "yc_letterbox_batch", "yc_format_detections", "yc_reserve_sms", "yc_copy_async",
+           "yc_xchg_bytes", "yc_xchg_alloc", "yc_xchg_open", "yc_xchg_close", "yc_xchg_free", "yc_xchg_push", "yc_xchg_wait",
+           "yc_xchg_state"]
 
 
 def _load():
@@ -73,6 +75,16 @@ def _load():
                                            C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_reserve_sms.argtypes = [C.c_int]
     lib.yc_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.yc_xchg_bytes.restype = C.c_size_t
+    lib.yc_xchg_bytes.argtypes = [C.c_int, C.c_int, C.c_size_t]
+    lib.yc_xchg_alloc.argtypes = [C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.yc_xchg_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.yc_xchg_close.argtypes = [C.c_void_p]
+    lib.yc_xchg_free.argtypes = [C.c_void_p]
+    lib.yc_xchg_push.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t,
+                                 C.c_void_p]
+    lib.yc_xchg_wait.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p]
+    lib.yc_xchg_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.yc_letterbox_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.yc_format_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]

@@ -144,3 +144,106 @@ class DetectionGather:
                 steps.append((hdr[:bs], hdr[2 * bs], rows))
             res.append(steps[0] if self.every == 1 else steps)
         return res
+
+
+class _DevMem:
+    """A device allocation made by the C library, viewed by torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerExchange:
+    """The detection exchange over NVLink peer memory (include/yc_b200.h, yc_xchg_*): per step ONE kernel of this rank
+    stores its message (header + the first `gather_rows` detection rows) into a slot of every rank's receive buffer and
+    raises a flag there; a second one-warp kernel waits for the flags of all ranks.  No NCCL call, no host work and no host
+    synchronisation per step; sequence numbers live on the device, so both kernels are captured inside the per-step CUDA
+    graph of PostBackbone (attach with `PostBackbone.attach_exchange`).  torch.distributed is used once, to hand the
+    CUDA IPC handles around.  A rank whose detections exceed `gather_rows` says so in its header
+    (offsets[-1] > gather_rows); callers fetch the remainder with `gather_detections`.
+
+    wait() for sequence number j declares every message before j consumed (their slots may be overwritten): read the
+    views of `unpack()` before waiting `slots - 1` steps further."""
+
+    def __init__(self, hdr_ints, bs, gather_rows, device, group=None, slots=4):
+        import ctypes as C
+
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.hdr_ints, self.bs, self.gather_rows, self.slots = int(hdr_ints), int(bs), int(gather_rows), int(slots)
+        self.msg_bytes = (self.hdr_ints * 4 + self.gather_rows * 28 + 15) // 16 * 16
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            buf = C.c_void_p()
+            handle = (C.c_uint8 * 64)()
+            _lib.check(_lib.lib.yc_xchg_alloc(self.world, self.slots, self.msg_bytes, C.byref(buf), handle), "yc_xchg_alloc")
+            self._buf = buf.value
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self._opened, ptrs = [], []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(self._buf)
+                    continue
+                p = C.c_void_p()
+                hb = (C.c_uint8 * 64).from_buffer_copy(h)
+                _lib.check(_lib.lib.yc_xchg_open(hb, C.byref(p)), f"yc_xchg_open (rank {r}: CUDA IPC / peer access)")
+                self._opened.append(p.value)
+                ptrs.append(p.value)
+            self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+            nbytes = _lib.lib.yc_xchg_bytes(self.world, self.slots, self.msg_bytes)
+            self._mem = _DevMem(self._buf, nbytes)
+            self.recv = torch.as_tensor(self._mem, device=self.device)   # uint8 view of this rank's receive buffer
+            dist.barrier(group=group)    # every rank has opened every buffer before anybody pushes
+
+    def push(self, msg, stream=None):
+        """Enqueue the push of `msg` (uint8 tensor: the prefix PostBackbone.message() returns, or the whole buffer).  The
+        i-th push of a rank (counting replays of a graph that captured it) carries sequence number i."""
+        s = self._C.c_void_p((stream or torch.cuda.current_stream(self.device)).cuda_stream)
+        self._lib.check(self._lib.lib.yc_xchg_push(msg.data_ptr(), self.hdr_ints, self.bs, self.gather_rows, self.peers.data_ptr(),
+                                                   self.world, self.rank, self.slots, self.msg_bytes, s), "yc_xchg_push")
+
+    def wait(self, stream=None, lag=0):
+        """Enqueue the wait for this rank's next un-awaited sequence number j: work queued behind it on `stream` sees the
+        messages of all ranks with that number.  lag = 1: a no-op unless this rank has pushed message j + 1 already
+        ("push(i); wait(lag=1)" every step awaits step i - 1 and never spins in the steady state)."""
+        s = self._C.c_void_p((stream or torch.cuda.current_stream(self.device)).cuda_stream)
+        self._lib.check(self._lib.lib.yc_xchg_wait(self.peers.data_ptr(), self.world, self.rank, self.slots, self.msg_bytes,
+                                                   int(lag), s), "yc_xchg_wait")
+
+    def state(self):
+        """(next push seq, next wait seq, error) read back from the device (synchronises the current stream)."""
+        out = (self._C.c_uint32 * 4)()
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.lib.yc_xchg_state(self._buf, self.world, self.slots, self.msg_bytes, out,
+                                                        self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                            "yc_xchg_state")
+        return int(out[0]), int(out[1]), int(out[3])
+
+    def unpack(self, seq):
+        """-> list over ranks of (counts [bs], total, rows [gather_rows, 7]) views of this rank's receive buffer for the
+        messages with sequence number `seq` (no copy; valid until wait() has been called slots - 1 more times)."""
+        slot = seq % self.slots
+        res = []
+        for r in range(self.world):
+            o = (slot * self.world + r) * self.msg_bytes
+            m = self.recv[o:o + self.msg_bytes]
+            hdr = m[:self.hdr_ints * 4].view(torch.int32)
+            rows = m[self.hdr_ints * 4:self.hdr_ints * 4 + self.gather_rows * 28].view(torch.float32).view(self.gather_rows, 7)
+            res.append((hdr[:self.bs], hdr[2 * self.bs], rows))
+        return res
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            for p in self._opened:
+                self._lib.lib.yc_xchg_close(self._C.c_void_p(p))
+            self._opened = []
+            dist.barrier(group=self.group)
+            if self._buf:
+                self.recv = None
+                self._lib.lib.yc_xchg_free(self._C.c_void_p(self._buf))
+                self._buf = None

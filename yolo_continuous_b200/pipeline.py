@@ -98,6 +98,7 @@ class PostBackbone:
         self._graphs = {}
         self._pgraphs = {}
         self._in_flight = False
+        self.exchange = None
         self._eager_dirty = False
         self._hp = None
         self.use_graph = use_graph and not self.overlap
@@ -207,6 +208,9 @@ class PostBackbone:
             if self.overlap:
                 _lib.check(_lib.lib.yc_nms_workspace_reset(C.byref(self.nms_params), self.ws.data_ptr(), self.ws.numel(),
                                                            C.c_void_p(tail.cuda_stream)), "yc_nms_workspace_reset")
+                if self.exchange is not None:
+                    self.exchange.push(self.msgs[c], tail)
+                    self.exchange.wait(tail, lag=1)
                 self.ev_tail[c].record(tail)
                 self._eager_dirty = True
             return
@@ -329,6 +333,21 @@ class PostBackbone:
                                                    m + 4 * self.bs, sp), "yc_nms_from_candidates")
         _lib.check(_lib.lib.yc_nms_workspace_reset(C.byref(self.nms_params), self.wss[c].data_ptr(), self.wss[c].numel(), sp),
                    "yc_nms_workspace_reset")
+        if self.exchange is not None:
+            # multi-GPU: this batch's detections go straight into every rank's receive buffer (one kernel, NVLink peer
+            # stores), then the messages of the PREVIOUS batch are awaited -- the one-step slack keeps the wait from
+            # ever spinning in the steady state while still bounding how far ranks can drift apart
+            self.exchange.push(self.msgs[c], stream)
+            self.exchange.wait(stream, lag=1)
+
+    def attach_exchange(self, exchange):
+        """Multi-GPU: `exchange` (parallel.PeerExchange built with this pipeline's hdr_ints / bs) receives every batch's
+        detections from the pipelined steps (submit / drain): the push and wait kernels run on the tail stream behind the
+        NMS kernels, inside the per-step CUDA graph.  After drain(), call exchange.wait() once more for the last batch."""
+        if exchange is not None and (exchange.hdr_ints != self.hdr_ints or exchange.bs != self.bs):
+            raise _lib.YcError("exchange was built for another message layout")
+        self.exchange = exchange
+        self._pgraphs.clear()
 
     def _pipelined_step(self, features, c, with_tail=True):
         """(captured) head of the current batch into workspace c  ||  NMS kernels of the previous batch (workspace
