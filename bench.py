@@ -570,6 +570,10 @@ def main():
     t1.record()
     sync_all()
     ms = t0.elapsed_time(t1)
+    if world > 1:   # max over ranks (also: every rank must derive the same step counts from it below)
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     # ---- the same K steps issued call by call (two streams, no graph) with the head kernel and the NMS kernels
     # bracketed by CUDA events on the streams they are launched on: per-kernel durations for the roofline ----------
     ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(K)]   # head start/end, NMS start/end
@@ -626,10 +630,6 @@ def main():
     sampler.stop()
     head_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
     tail_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in ev)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = world * args.bs * K / (ms / 1e3)
     counts_host = pipe.meta[:args.bs].cpu().numpy()
     n_det = int(counts_host.sum())

@@ -102,6 +102,9 @@ typedef struct yc_head_desc {
     float *z;           /* [bs, sum(na*H*W), no_out] decoded rows (no_out = no, IBin: no - 2*(bin_count+1) + 2),
                            NULL for YC_HEAD_RAW */
     const float *bins;  /* IBin: device [bin_count] (SigmoidBin.bins buffer) */
+    int32_t x_channels_last; /* 1: the feature maps are [bs, H, W, K] (torch channels_last, e.g. the output of a re-parameterised
+                                RepConv, nets/common.py:561-614, run channels-last): the head GEMM reads them as a K-major
+                                operand.  bf16 maps on the tcgen05 path only (YC_ERR_UNSUPPORTED otherwise). */
 } yc_head_desc;
 
 /* IDetect/IAuxDetect/IBin.forward (eval and train) for all levels in one call.
@@ -233,6 +236,14 @@ YC_API int yc_format_detections(const float *rows, const int32_t *offsets, int b
                          int image_hw_stride, int32_t *box_xyxy, float *conf, int32_t *label, yc_stream_t stream);
 
 YC_API int yc_box_iou(const float *b1, int n, const float *b2, int m, float *out, yc_stream_t stream);
+/* Matching step of a batched on-device evaluator (the reference has none -- the IoU is its
+ * box_iou, utils/bbox.py:62-72).  det_rows [total,7] + det_offsets [bs+1] as yc_nms_batched / yc_detect_fused leave them
+ * (per image: class ascending, score descending); gt_boxes [n_gt,4] in the detections' coordinate convention, gt_labels
+ * [n_gt] int32, gt_offsets [bs+1] (at most 2048 boxes per image are considered).  For every IoU threshold t a detection
+ * takes the unmatched ground-truth box of its class with the highest IoU >= thr: tp [n_thr, total] uint8. */
+YC_API int yc_match_detections(const float *det_rows, const int32_t *det_offsets, int bs, int total, const float *gt_boxes,
+                        const int32_t *gt_labels, const int32_t *gt_offsets, const float *iou_thrs, int n_thr, uint8_t *tp,
+                        yc_stream_t stream);
 YC_API int yc_cvt_bbox(const float *in, int n, int flag, float *out, yc_stream_t stream);
 
 #ifdef __cplusplus

@@ -54,3 +54,26 @@ def assert_close_scaled(got, ref, scale, rtol, what=""):
         i = np.unravel_index(np.argmax(err / tol), err.shape)
         raise AssertionError(f"{what}: {bad.sum()} of {bad.size} outside rtol={rtol}; worst at {i}: "
                              f"got {got[i]!r} ref {ref[i]!r} err {err[i]:.3e} tol {tol[i]:.3e}")
+
+
+def make_rep(c1, c2, stride):
+    """A RepConv block in the reference's layout (nets/common.py:440-472), rebuilt for the tests (the reference module
+    itself cannot travel to the GPU box)."""
+    import torch
+    from torch import nn
+
+    class Rep(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.deploy, self.groups, self.in_channels, self.out_channels = False, 1, c1, c2
+            self.act = nn.SiLU()
+            self.rbr_identity = nn.BatchNorm2d(c1) if c2 == c1 and stride == 1 else None
+            self.rbr_dense = nn.Sequential(nn.Conv2d(c1, c2, 3, stride, 1, bias=False), nn.BatchNorm2d(c2))
+            self.rbr_1x1 = nn.Sequential(nn.Conv2d(c1, c2, 1, stride, 0, bias=False), nn.BatchNorm2d(c2))
+
+        def forward(self, x):
+            if hasattr(self, "rbr_reparam"):
+                return self.act(self.rbr_reparam(x))
+            return self.act(self.rbr_dense(x) + self.rbr_1x1(x) + (0 if self.rbr_identity is None else self.rbr_identity(x)))
+
+    return Rep().eval()

@@ -1016,3 +1016,86 @@ def test_tcgen05_fp32_split_full_size_vs_exact_kernel():
         assert float(((a_ - b_).abs() / b_.abs().clamp_min(1.0)).max()) < 1e-5
     rel = (z_t - z_g).abs() / z_g.abs().clamp_min(8.0)
     assert float(rel.max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# re-parameterised RepConv -> channels-last maps -> head GEMM with a K-major A operand
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["repconv_identity", "repconv_noid"])
+def test_repconv_reparam_on_device_vs_reference(name):
+    """RepConv.fuse_repvgg_block (nets/common.py:561-614) as device tensor algebra against the reference's fused weight /
+    bias / output (fixture from the unmodified reference)."""
+    from helpers import make_rep
+    from yolo_continuous_b200.nets.common import fuse_repvgg_block, repconv_equivalent
+    fx = load(name)
+    c1, c2, s_ = (int(v) for v in fx["c"])
+    rep = make_rep(c1, c2, s_)
+    rep.load_state_dict({k[4:].replace("__", "."): torch.from_numpy(v) for k, v in fx.items() if k.startswith("sd__")})
+    rep = rep.to(DEV)
+    x = torch.from_numpy(fx["x"]).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            w, b = repconv_equivalent(rep)
+            assert w.is_cuda
+            np.testing.assert_allclose(w.cpu().numpy(), fx["weight"], rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(b.cpu().numpy(), fx["bias"], rtol=2e-6, atol=1e-6)
+            fuse_repvgg_block(rep)
+            assert rep.deploy and rep.rbr_dense is None
+            np.testing.assert_allclose(rep(x).cpu().numpy(), fx["after"], rtol=1e-4, atol=1e-5)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_channels_last_maps_feed_the_head_k_major():
+    """Fused RepConv blocks run channels-last in bf16; their outputs go to the head WITHOUT a layout change (A operand
+    K-major).  Same z, raw maps and detections, bit for bit, as the NCHW route; both fused kernels."""
+    import os
+    from helpers import make_rep
+    from yolo_continuous_b200 import _lib
+    from yolo_continuous_b200.nets.common import fuse_repvgg_block
+    from yolo_continuous_b200.pipeline import PostBackbone
+    ch, shapes, bs = (64, 128, 256), [(40, 40), (20, 20), (12, 12)], 5
+    torch.manual_seed(3)
+    reps = []
+    for c in ch:
+        rep = make_rep(c, c, 1)
+        for m_ in rep.modules():
+            if isinstance(m_, torch.nn.BatchNorm2d):
+                m_.running_var.uniform_(0.5, 1.5)
+                m_.running_mean.normal_(0, 0.3)
+        reps.append(fuse_repvgg_block(rep.to(DEV)).to(torch.bfloat16).to(memory_format=torch.channels_last))
+    g = torch.Generator(device=DEV).manual_seed(8)
+    with torch.no_grad():
+        feats = [rep(torch.randn(bs, c, h, w, generator=g, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+                 for rep, c, (h, w) in zip(reps, ch, shapes)]
+    for f in feats:
+        assert f.is_contiguous(memory_format=torch.channels_last) and not f.is_contiguous()
+    nchw = [f.contiguous() for f in feats]
+    head = _bench_like_head(80, ch, 3).to(DEV)
+    head.head_path = _lib.YC_PATH_TCGEN05
+    z_cl, raw_cl = head(list(feats))
+    z, raw = head(list(nchw))
+    assert torch.equal(z_cl, z)
+    for a_, b_ in zip(raw_cl, raw):
+        assert torch.equal(a_, b_)
+    res = []
+    for cl, two_cta in ((False, "1"), (True, "1"), (True, "0")):
+        os.environ["YC_TC_2CTA"] = two_cta
+        try:
+            pipe = PostBackbone(head, bs, shapes, torch.bfloat16, (320, 320), (240, 320), True, 0.25, 0.45, DEV,
+                                use_graph=False, channels_last=cl)
+            rows, idx, counts, offsets = pipe.run_device(feats if cl else nchw)
+            assert pipe.fused
+            tot = int(offsets[-1])
+            res.append((rows[:tot].clone(), idx[:tot].clone(), counts.clone()))
+        finally:
+            os.environ.pop("YC_TC_2CTA", None)
+    assert int(res[0][2].sum()) > 20
+    for r in res[1:]:
+        for a_, b_ in zip(r, res[0]):
+            assert torch.equal(a_, b_)
+    with pytest.raises(_lib.YcError):
+        PostBackbone(head, bs, shapes, torch.bfloat16, (320, 320), (240, 320), True, 0.25, 0.45, DEV, channels_last=True) \
+            .run_device(nchw)

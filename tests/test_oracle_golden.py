@@ -143,26 +143,12 @@ def test_repconv_reparam_vs_reference(name):
     """RepConv.fuse_repvgg_block (nets/common.py:565-614): the collapsed 3x3 weight / bias equal the reference's bit for
     bit and the fused block reproduces its output (host logic: runs wherever the parameters live)."""
     import torch
-    from torch import nn
+    from helpers import make_rep
     from yolo_continuous_b200.nets.common import fuse_repvgg_block, repconv_equivalent
     fx = load(name)
     c1, c2, s_ = (int(v) for v in fx["c"])
 
-    class Rep(nn.Module):   # the reference's layout (nets/common.py:440-472), rebuilt here from the fixture
-        def __init__(self):
-            super().__init__()
-            self.deploy, self.groups, self.in_channels, self.out_channels = False, 1, c1, c2
-            self.act = nn.SiLU()
-            self.rbr_identity = nn.BatchNorm2d(c1) if c2 == c1 and s_ == 1 else None
-            self.rbr_dense = nn.Sequential(nn.Conv2d(c1, c2, 3, s_, 1, bias=False), nn.BatchNorm2d(c2))
-            self.rbr_1x1 = nn.Sequential(nn.Conv2d(c1, c2, 1, s_, 0, bias=False), nn.BatchNorm2d(c2))
-
-        def forward(self, x):
-            if hasattr(self, "rbr_reparam"):
-                return self.act(self.rbr_reparam(x))
-            return self.act(self.rbr_dense(x) + self.rbr_1x1(x) + (0 if self.rbr_identity is None else self.rbr_identity(x)))
-
-    rep = Rep().eval()
+    rep = make_rep(c1, c2, s_)   # the reference's layout (nets/common.py:440-472), rebuilt from the fixture
     rep.load_state_dict({k[4:].replace("__", "."): torch.from_numpy(v) for k, v in fx.items() if k.startswith("sd__")})
     x = torch.from_numpy(fx["x"])
     with torch.no_grad():

@@ -25,7 +25,7 @@ class HeadDesc(C.Structure):
                 ("nl", C.c_int32), ("na", C.c_int32), ("no", C.c_int32),
                 ("bin_count", C.c_int32), ("bs", C.c_int32),
                 ("level", HeadLevel * YC_MAX_LEVELS),
-                ("z", C.c_void_p), ("bins", C.c_void_p)]
+                ("z", C.c_void_p), ("bins", C.c_void_p), ("x_channels_last", C.c_int32)]
 
 
 class NmsParams(C.Structure):
@@ -43,7 +43,7 @@ EXPORTS = ["yc_last_error", "yc_version", "yc_device_check", "yc_head_pack_bytes
            "yc_detect_fused_head", "yc_nms_from_candidates", "yc_nms_workspace_reset", "yc_detect_fused_head_noreset",
            "yc_letterbox_batch", "yc_format_detections", "yc_reserve_sms", "yc_copy_async",
            "yc_xchg_bytes", "yc_xchg_alloc", "yc_xchg_open", "yc_xchg_close", "yc_xchg_free", "yc_xchg_push", "yc_xchg_wait",
-           "yc_xchg_state"]
+           "yc_xchg_state", "yc_match_detections"]
 
 
 def _load():
@@ -91,6 +91,8 @@ def _load():
     lib.yc_nms_single.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.c_void_p, C.c_void_p]
     lib.yc_box_iou.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.yc_match_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.yc_cvt_bbox.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return lib
 

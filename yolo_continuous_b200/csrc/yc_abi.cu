@@ -31,19 +31,64 @@ int launch_head_generic(const yc_head_desc *d, int rows_total, const int *row_of
 int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_off, unsigned *left_mask,
                         const FusedDetect *fused, cudaStream_t stream);
 
-// utils/bbox.py:62-72
-__global__ void box_iou_kernel(const float4 *__restrict__ b1, int n, const float4 *__restrict__ b2, int m,
-                               float *__restrict__ out)
+// utils/bbox.py:62-72: area(a), area(b), clamped intersection, inter / (area_a + area_b - inter), binary32, no FMA
+__device__ __forceinline__ float box_iou_f(const float4 a, const float4 b)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)n * m) return;
-    const float4 a = b1[i / m], b = b2[i % m];
     const float a1 = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
     const float a2 = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
     const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
     const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
     const float inter = __fmul_rn(w, h);
-    out[i] = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a1, a2), inter));
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(a1, a2), inter));
+}
+
+__global__ void box_iou_kernel(const float4 *__restrict__ b1, int n, const float4 *__restrict__ b2, int m,
+                               float *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * m) return;
+    out[i] = box_iou_f(b1[i / m], b2[i % m]);
+}
+
+// Batched evaluator, matching step (the reference has no evaluator -- the IoU is its
+// utils/bbox.py:62-72): one warp per (image, IoU threshold).  The detections of an image are visited in the order the NMS
+// leaves them (class ascending, score descending within a class: the order greedy matching needs); each takes the
+// not yet matched ground-truth box of its class with the highest IoU >= thr (ties: the first).  tp[t][d] = 1 if matched.
+constexpr int EVAL_MAX_GT = 2048;   // ground-truth boxes per image (matched flags live in shared memory)
+__global__ void __launch_bounds__(32) match_kernel(const float *__restrict__ det_rows, const int *__restrict__ det_off,
+                                                   const float4 *__restrict__ gt_box, const int *__restrict__ gt_cls,
+                                                   const int *__restrict__ gt_off, const float *__restrict__ thrs, int total,
+                                                   unsigned char *__restrict__ tp)
+{
+    __shared__ unsigned int taken[EVAL_MAX_GT / 32];
+    const int b = blockIdx.x, t = blockIdx.y, lane = threadIdx.x;
+    const int d0 = det_off[b], d1 = det_off[b + 1], g0 = gt_off[b], ng = min(gt_off[b + 1] - g0, EVAL_MAX_GT);
+    const float thr = thrs[t];
+    for (int i = lane; i < EVAL_MAX_GT / 32; i += 32) taken[i] = 0u;
+    __syncwarp();
+    for (int d = d0; d < d1; ++d) {
+        const float *r = det_rows + (size_t)d * 7;
+        const float4 db = make_float4(r[0], r[1], r[2], r[3]);
+        const int cls = (int)r[6];
+        float best = -1.0f;
+        int bi = -1;
+        for (int g = lane; g < ng; g += 32) {
+            if (gt_cls[g0 + g] != cls || (taken[g >> 5] >> (g & 31) & 1u)) continue;
+            const float iou = box_iou_f(db, gt_box[g0 + g]);
+            if (iou >= thr && iou > best) { best = iou; bi = g; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {   // highest IoU wins, ties go to the lower ground-truth index
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (ov > best || (ov == best && (bi < 0 || oi < bi)))) { best = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            tp[(size_t)t * total + d] = bi >= 0 ? 1 : 0;
+            if (bi >= 0) taken[bi >> 5] |= 1u << (bi & 31);
+        }
+        __syncwarp();
+    }
 }
 
 // utils/bbox.py:29-59 (tensor branch: the result starts as a clone of the input)
@@ -255,4 +300,19 @@ extern "C" int yc_detect_fused(const yc_head_desc *d, const yc_nms_params *p, vo
     const int rc = yc_detect_fused_head(d, p, workspace, workspace_bytes, stream);
     if (rc != YC_OK) return rc;
     return yc_nms_from_candidates(p, workspace, workspace_bytes, out_rows, out_idx, out_counts, out_offsets, stream);
+}
+
+extern "C" int yc_match_detections(const float *det_rows, const int32_t *det_offsets, int bs, int total, const float *gt_boxes,
+                                   const int32_t *gt_labels, const int32_t *gt_offsets, const float *iou_thrs, int n_thr,
+                                   uint8_t *tp, yc_stream_t stream)
+{
+    if (bs <= 0 || n_thr <= 0 || total <= 0) return YC_OK;
+    YC_REQUIRE(det_rows && det_offsets && gt_boxes && gt_labels && gt_offsets && iou_thrs && tp, YC_ERR_INVALID,
+               "yc_match_detections: null argument");
+    YC_REQUIRE(((uintptr_t)gt_boxes & 15) == 0, YC_ERR_INVALID, "yc_match_detections: gt_boxes must be 16-byte aligned");
+    YC_REQUIRE(bs <= 65535 && n_thr <= 65535, YC_ERR_UNSUPPORTED, "yc_match_detections: grid too large");
+    match_kernel<<<dim3(bs, n_thr), 32, 0, (cudaStream_t)stream>>>(det_rows, det_offsets, (const float4 *)gt_boxes, gt_labels,
+                                                                  gt_offsets, iou_thrs, total, tp);
+    YC_CUDA(cudaGetLastError());
+    return YC_OK;
 }

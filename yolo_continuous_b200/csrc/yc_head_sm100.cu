@@ -23,7 +23,9 @@ namespace yc {
 
 // DBG instantiations honour the YC_TC_DEBUG timing switches (bit 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA,
 // 8 print clock64 wait statistics of CTA 0); the production instantiation carries none of that code.
-template <int BK, bool DBG>
+// AK: the feature maps are channels-last ([bs, H, W, K], e.g. the output of a channels-last RepConv): A is then a K-major
+// operand, one {64 k, 128 px} TMA box per stage, instead of the MN-major operand NCHW maps give.
+template <int BK, bool DBG, bool AK>
 __global__ void __maxnreg__(TC_MAX_REGS)
 head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
@@ -111,8 +113,15 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         mbar_arrive(&full_bar[stage]);
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], tx);
-                        tma_load_3d(sa, ma, &full_bar[stage], tc.p0, kb * TC_BK, tc.b);
-                        tma_load_3d(sa + TC_A_BYTES / 2, ma, &full_bar[stage], tc.p0 + 64, kb * TC_BK, tc.b);
+                        if (AK) {   // rows = pixels of the flat [bs*HW, K] view; a tile's tail rows may belong to the next image
+#pragma unroll
+                            for (int j = 0; j < BK / 64; ++j)
+                                tma_load_2d(sa + j * (TC_A_BYTES / (BK / 64)), ma, &full_bar[stage], kb * TC_BK + j * 64,
+                                            tc.b * P.lv[tc.lv].HW + tc.p0);
+                        } else {
+                            tma_load_3d(sa, ma, &full_bar[stage], tc.p0, kb * TC_BK, tc.b);
+                            tma_load_3d(sa + TC_A_BYTES / 2, ma, &full_bar[stage], tc.p0 + 64, kb * TC_BK, tc.b);
+                        }
                         if (load_b) {
 #pragma unroll
                             for (int j = 0; j < BK / 64; ++j)
@@ -139,7 +148,8 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // B: K-major SW128, one box per 64 k: 8-row groups SBO = 1024 B apart; k16 step = 32 B inside the 128-B row
         // The start-address field holds (address >> 4) in the low 14 bits: stage / k offsets are plain adds.
         const uint32_t s0 = smem_addr(stage_base);
-        const uint64_t da0 = smem_desc(s0, TC_A_BYTES / 2, 1024, SWZ_128B);
+        // (AK: A is K-major like B -- one {64 k, 128 px} box per 64 k: 8-row groups SBO = 1024 B apart, k16 step = 32 B)
+        const uint64_t da0 = AK ? smem_desc(s0, 16, 1024, SWZ_128B) : smem_desc(s0, TC_A_BYTES / 2, 1024, SWZ_128B);
         const uint64_t db0 = smem_desc(s0 + TC_A_BYTES, 16, 1024, SWZ_128B);
         const uint32_t idesc = P.idesc;
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
@@ -162,7 +172,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                     if (!skip_mma) {
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k)
-                            mma_f16(tmem_d, da0 + so + (uint64_t)((k * 2048) >> 4),
+                            mma_f16(tmem_d, da0 + so + (uint64_t)((AK ? (k / 4) * (TC_BM * 128) + (k % 4) * 32 : k * 2048) >> 4),
                                     db0 + so + (uint64_t)(((k / 4) * TC_B_SLOT + (k % 4) * 32) >> 4), idesc,
                                     (uint32_t)((kb | k) != 0));
                     }
@@ -278,6 +288,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         YC_CUDA(cudaGetDevice(&dev));
         YC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    YC_REQUIRE(!(d->x_channels_last && d->x_dtype != YC_BF16), YC_ERR_UNSUPPORTED, "tcgen05 head: channels-last maps must be bf16");
     if (d->x_dtype == YC_F32)   // float32 maps: fp16 hi/lo split, three MMAs per k-step, float32-grade result
         return launch_head_split(d, rows_total, row_off, left_mask, (void *)enc, g_num_sms - g_reserved_sms > 0 ? g_num_sms - g_reserved_sms : 1,
                                  stream);
@@ -315,7 +326,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     for (int i = 0; i < d->nl; ++i) {
         const yc_head_level &lv = d->level[i];
         const size_t HW = (size_t)lv.H * lv.W;
-        const bool ok = (HW * 2) % 16 == 0 && ((size_t)lv.K * 2) % 16 == 0 && ((uintptr_t)lv.x & 15) == 0 &&
+        const bool ok = (d->x_channels_last || (HW * 2) % 16 == 0) && ((size_t)lv.K * 2) % 16 == 0 && ((uintptr_t)lv.x & 15) == 0 &&
                         (d->kind != YC_HEAD_RAW || lv.raw) && !(fused && lv.raw);
         if (ok) fit |= 1u << i;
         else set_error("level %d (K=%d, H*W=%zu) does not meet the TMA alignment rules", i, lv.K, HW);
@@ -346,7 +357,9 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         P.bins = d->bins;
     }
     P.z = d->z;
-    P.idesc = instr_desc_f16(/*bf16*/ 1, /*A MN-major*/ 1, /*B K-major*/ 0, (uint32_t)tile_px, (uint32_t)npad);
+    P.idesc = instr_desc_f16(/*bf16*/ 1, /*A: MN-major (NCHW) or K-major (channels-last)*/ d->x_channels_last ? 0 : 1,
+                             /*B K-major*/ 0, (uint32_t)tile_px, (uint32_t)npad);
+    P.a_kmajor = d->x_channels_last ? 1 : 0;
     P.b_box_bytes = (uint32_t)(pair ? npad / 2 : npad) * 64 * 2;
     P.b_slot_bytes = b_slot_bytes;
     P.slab_bytes = slab_bytes;
@@ -378,7 +391,15 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         L.stride_y = lv.stride_y > 0.f ? lv.stride_y : lv.stride;
         for (int j = 0; j < YC_MAX_ANCHORS * 2; ++j) L.anchor_wh[j] = lv.anchor_wh[j];
         tiles += pair ? (L.n_boxes + 3) / 4 : d->bs * L.tiles_per_img * n_groups;
-        {   // A: X [bs, K, HW] bf16, box {64 px, 64 k, 1}
+        if (d->x_channels_last) {   // A: X [bs*HW, K] bf16 (channels-last), box {64 k, 128 px} (pair kernel: 64 px)
+            cuuint64_t gdim[2] = {(cuuint64_t)lv.K, (cuuint64_t)d->bs * HW};
+            cuuint64_t gstr[1] = {(cuuint64_t)lv.K * 2};
+            cuuint32_t box[2] = {64, (cuuint32_t)(pair ? 64 : TC_BM)}, est[2] = {1, 1};
+            CUresult r = enc(&maps.a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)lv.x, gdim, gstr, box, est,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            YC_REQUIRE(r == CUDA_SUCCESS, YC_ERR_CUDA, "cuTensorMapEncodeTiled(A channels-last, level %d) failed: %d", i, (int)r);
+        } else {   // A: X [bs, K, HW] bf16, box {64 px, 64 k, 1}
             cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)lv.K, (cuuint64_t)d->bs};
             cuuint64_t gstr[2] = {(cuuint64_t)HW * 2, (cuuint64_t)HW * lv.K * 2};
             cuuint32_t box[3] = {64, (cuuint32_t)bk, 1}, est[3] = {1, 1, 1};
@@ -405,8 +426,13 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     const int sms = g_num_sms - g_reserved_sms > 0 ? g_num_sms - g_reserved_sms : 1;
     const int grid = tiles < sms ? tiles : sms;
     const int threads = TC_NON_EPI_THREADS + 32 * epi_warps;
-    void (*kern)(const TcMaps, const TcParams) = P.debug ? (bk == 128 ? head_tc_kernel<128, true> : head_tc_kernel<64, true>)
-                                                         : (bk == 128 ? head_tc_kernel<128, false> : head_tc_kernel<64, false>);
+    void (*kern)(const TcMaps, const TcParams);
+    if (P.a_kmajor)
+        kern = P.debug ? (bk == 128 ? head_tc_kernel<128, true, true> : head_tc_kernel<64, true, true>)
+                       : (bk == 128 ? head_tc_kernel<128, false, true> : head_tc_kernel<64, false, true>);
+    else
+        kern = P.debug ? (bk == 128 ? head_tc_kernel<128, true, false> : head_tc_kernel<64, true, false>)
+                       : (bk == 128 ? head_tc_kernel<128, false, false> : head_tc_kernel<64, false, false>);
     YC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kern<<<grid, threads, smem_bytes, stream>>>(maps, P);
     YC_CUDA(cudaGetLastError());

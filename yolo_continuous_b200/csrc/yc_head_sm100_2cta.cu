@@ -45,7 +45,8 @@ __device__ __forceinline__ void ring_advance(int &s, uint32_t &parity, int n, in
     while (s >= depth) { s -= depth; parity ^= 1u; }
 }
 
-template <bool DBG>
+// AK: channels-last feature maps (A K-major): each 64-pixel box is one {64 k, 64 px} TMA box of the flat [bs*HW, K] view
+template <bool DBG, bool AK>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(TC_MAX_REGS)
 head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
@@ -123,8 +124,14 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                         if (rank == 0) mbar_arrive(&R.a_full[sa]);
                     } else {
                         if (rank == 0) mbar_arrive_expect_tx(&R.a_full[sa], 2u * (uint32_t)T2_A_BYTES);
-                        tma_load_3d_pair(dst, ma, &R.a_full[sa], p0, kb * T2_BK, b0);
-                        tma_load_3d_pair(dst + T2_A_BYTES / 2, ma, &R.a_full[sa], p1, kb * T2_BK, b1);
+                        if (AK) {   // image index bs (past the end) -> rows past the tensor: TMA zero-fills
+                            const int HW = P.lv[tc.lv].HW;
+                            tma_load_2d_pair(dst, ma, &R.a_full[sa], kb * T2_BK, b0 * HW + p0);
+                            tma_load_2d_pair(dst + T2_A_BYTES / 2, ma, &R.a_full[sa], kb * T2_BK, b1 * HW + p1);
+                        } else {
+                            tma_load_3d_pair(dst, ma, &R.a_full[sa], p0, kb * T2_BK, b0);
+                            tma_load_3d_pair(dst + T2_A_BYTES / 2, ma, &R.a_full[sa], p1, kb * T2_BK, b1);
+                        }
                     }
                 }
                 __syncwarp();
@@ -175,7 +182,8 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
             const int me = warp == 3 ? 1 : 0;
             int sa = 0, it = 0, resident = -1, g = 0;   // g: global k-block counter of the pair
             uint32_t pa = 0, pbits = 0;
-            const uint64_t da0 = smem_desc(smem_addr(R.a_ring), T2_A_BYTES / 2, 1024, SWZ_128B);
+            const uint64_t da0 = AK ? smem_desc(smem_addr(R.a_ring), 16, 1024, SWZ_128B)
+                                    : smem_desc(smem_addr(R.a_ring), T2_A_BYTES / 2, 1024, SWZ_128B);
             const uint64_t db0 = smem_desc(smem_addr(R.b_slots), 16, 1024, SWZ_128B);
             const uint32_t idesc = P.idesc;
             volatile int *turn = (volatile int *)(R.tmem_ptr + 1);
@@ -211,7 +219,7 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                             if (!skip_mma) {
 #pragma unroll
                                 for (int k = 0; k < T2_BK / 16; ++k)
-                                    mma_f16_pair(tmem_d, da + (uint64_t)((k * 2048) >> 4),
+                                    mma_f16_pair(tmem_d, da + (uint64_t)((AK ? k * 32 : k * 2048) >> 4),
                                                  db + (uint64_t)(((k / 4) * T2_B_BOX + (k % 4) * 32) >> 4), idesc,
                                                  (uint32_t)((kb | k) != 0));
                             }
@@ -298,7 +306,8 @@ int launch_head_tc2(const TcMaps &maps, TcParams &P, int num_sms, cudaStream_t s
     const size_t smem_bytes = fixed + (size_t)stages * T2_A_BYTES;
     YC_REQUIRE(smem_bytes <= 227 * 1024, YC_ERR_UNSUPPORTED, "2-CTA head: needs %zu bytes of shared memory", smem_bytes);
     P.stages = stages;
-    void (*kern)(const TcMaps, const TcParams) = P.debug ? head_tc2_kernel<true> : head_tc2_kernel<false>;
+    void (*kern)(const TcMaps, const TcParams) = P.a_kmajor ? (P.debug ? head_tc2_kernel<true, true> : head_tc2_kernel<false, true>)
+                                                            : (P.debug ? head_tc2_kernel<true, false> : head_tc2_kernel<false, false>);
     YC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int pairs = num_sms / 2;
     if (P.total_tiles < pairs) pairs = P.total_tiles;

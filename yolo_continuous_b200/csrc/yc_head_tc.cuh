@@ -73,6 +73,7 @@ struct TcParams {
     uint32_t slab_bytes;       // per epilogue warp: 32*no*4 (z slab) or TC_QUEUE_ROWS*nc*4 (fused survivor queue)
     int debug;                 // YC_TC_DEBUG bits (timing experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA
     int stages;                // depth of the smem ring
+    int a_kmajor;              // feature maps are channels-last: A is a K-major operand
     // fused mode (yc_detect_fused): the epilogue thresholds and emits NMS candidates, z is never written
     int fused;
     int nc;

@@ -100,14 +100,19 @@ class HeadBase(nn.Module):
         else:
             raise _lib.YcError(f"unsupported feature-map dtype {x0.dtype}: use float32 or bfloat16")
         dev, bs = x0.device, x0.shape[0]
+        # channels-last bf16 maps (e.g. the output of a channels-last RepConv) are consumed as they are: the tcgen05
+        # kernels read them as a K-major operand; anything else is taken as NCHW
+        nhwc = xdt == _lib.YC_BF16 and self.head_path != _lib.YC_PATH_GENERIC and all(
+            not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last) and t.shape[1] % 8 == 0 for t in xs)
         d = _lib.HeadDesc()
         d.kind, d.path, d.x_dtype = kind, self.head_path, xdt
+        d.x_channels_last = 1 if nhwc else 0
         d.nl, d.na, d.no, d.bin_count, d.bs = nl, self.na, self.no, bin_count, bs
         keep = []
         raws, rows = [], 0
         with torch.cuda.device(dev):
             for i in range(nl):
-                x = xs[i].contiguous()
+                x = xs[i] if nhwc else xs[i].contiguous()
                 keep.append(x)
                 _, k, h, w = x.shape
                 if k != convs[i].weight.shape[1]:

@@ -23,11 +23,16 @@ from . import _lib
 class PostBackbone:
     def __init__(self, head, bs, shapes, dtype=torch.bfloat16, input_shape=(640, 640), image_shape=(640, 640),
                  letterbox_image=True, conf_thres=0.25, nms_thres=0.45, device="cuda:0", use_graph=True,
-                 spec_rows=65536, fused=True, double_buffer=False, overlap=False):
+                 spec_rows=65536, fused=True, double_buffer=False, overlap=False, channels_last=False):
         self.head, self.bs, self.shapes = head, bs, [tuple(s) for s in shapes]
         self.device = torch.device(device)
         self.dtype = dtype
         self.nc, self.na, self.no = head.nc, head.na, head.no
+        # channels_last: the feature maps are torch channels_last tensors ([bs, H, W, K] in memory, e.g. straight out of a
+        # channels-last neck): the head GEMM reads them as a K-major operand (bf16 maps, tcgen05 path only)
+        self.channels_last = bool(channels_last)
+        if self.channels_last and dtype != torch.bfloat16:
+            raise _lib.YcError("channels_last=True needs bfloat16 feature maps")
         if not hasattr(head, "m") or head.no != head.nc + 5:
             raise _lib.YcError("PostBackbone drives IDetect/IAuxDetect-style heads (no = nc + 5)")
         self.nl = len(self.shapes)
@@ -35,7 +40,9 @@ class PostBackbone:
         self.rows = sum(self.na * h * w for h, w in self.shapes)
         self.ch = [head.m[i].weight.shape[1] for i in range(self.nl)]
         with torch.cuda.device(dev):
-            self.x_dev = [torch.empty((bs, c, h, w), dtype=dtype, device=dev) for c, (h, w) in zip(self.ch, self.shapes)]
+            fmt = torch.channels_last if self.channels_last else torch.contiguous_format
+            self.x_dev = [torch.empty((bs, c, h, w), dtype=dtype, device=dev, memory_format=fmt)
+                          for c, (h, w) in zip(self.ch, self.shapes)]
             self.z = torch.empty((bs, self.rows, self.no), dtype=torch.float32, device=dev)
             # Output message(s): [counts (bs) | offsets (bs+1) | pad] int32 header followed by the detection rows
             # [bs*rows, 7] fp32 in ONE allocation, so that a fixed-size prefix (header + the first `gather_rows`
@@ -58,7 +65,7 @@ class PostBackbone:
             self.ev_tail = [torch.cuda.Event() for _ in range(n_ws)]
             hw = np.asarray(image_shape, dtype=np.int32).reshape(-1, 2)
             self.image_hw = torch.from_numpy(np.ascontiguousarray(hw)).to(dev)
-            self.x_host = [torch.empty(t.shape, dtype=dtype).pin_memory() for t in self.x_dev]
+            self.x_host = [torch.empty(t.shape, dtype=dtype, memory_format=fmt).pin_memory() for t in self.x_dev]
             self.spec_rows = min(spec_rows, bs * self.rows)
             self.meta_host = torch.empty((2 * bs + 1,), dtype=torch.int32).pin_memory()
             self.rows_host = torch.empty((bs * self.rows, 7), dtype=torch.float32).pin_memory() \
@@ -68,6 +75,7 @@ class PostBackbone:
         d.kind, d.path = _lib.YC_HEAD_IDETECT, head.head_path
         d.x_dtype = _lib.YC_BF16 if dtype == torch.bfloat16 else _lib.YC_F32
         d.nl, d.na, d.no, d.bs = self.nl, self.na, self.no, bs
+        d.x_channels_last = 1 if self.channels_last else 0
         self._blobs = []
         for i, (h, w) in enumerate(self.shapes):
             blob = head._blob((id(head.m[i]),), head.m[i], head.ia[i], head.im[i], dev)
@@ -169,10 +177,15 @@ class PostBackbone:
         return self.msgs[self.cur ^ 1 if previous else self.cur][:self.hdr_ints * 4 + gather_rows * 28]
 
     # ---- device path -----------------------------------------------------------------------
+    def _check(self, i, x):
+        ok = x.is_contiguous(memory_format=torch.channels_last) if self.channels_last else x.is_contiguous()
+        if x.dtype != self.dtype or tuple(x.shape) != tuple(self.x_dev[i].shape) or not ok:
+            raise _lib.YcError(f"level {i}: expected {'channels-last' if self.channels_last else 'contiguous'} "
+                               f"{tuple(self.x_dev[i].shape)} {self.dtype}")
+
     def _launch(self, features, head_events=None):
         for i, x in enumerate(features):
-            if x.dtype != self.dtype or tuple(x.shape) != tuple(self.x_dev[i].shape) or not x.is_contiguous():
-                raise _lib.YcError(f"level {i}: expected contiguous {tuple(self.x_dev[i].shape)} {self.dtype}")
+            self._check(i, x)
             self.desc.level[i].x = x.data_ptr()
         s = _lib.stream_ptr(self.device)
         m = self.meta.data_ptr()
@@ -287,8 +300,7 @@ class PostBackbone:
             # call), so that results an earlier eager run_device() call left in the other output buffer stay untouched
             if not self._in_flight:
                 for i, x in enumerate(features):
-                    if x.dtype != self.dtype or tuple(x.shape) != tuple(self.x_dev[i].shape) or not x.is_contiguous():
-                        raise _lib.YcError(f"level {i}: expected contiguous {tuple(self.x_dev[i].shape)} {self.dtype}")
+                    self._check(i, x)
                 self._pipelined_step(features, c, with_tail=False)
                 self._in_flight = True
                 return None
@@ -296,8 +308,7 @@ class PostBackbone:
             g = self._pgraphs.get(key)
             if g is None:
                 for i, x in enumerate(features):
-                    if x.dtype != self.dtype or tuple(x.shape) != tuple(self.x_dev[i].shape) or not x.is_contiguous():
-                        raise _lib.YcError(f"level {i}: expected contiguous {tuple(self.x_dev[i].shape)} {self.dtype}")
+                    self._check(i, x)
                 torch.cuda.current_stream().wait_event(self.ev_tail[0])
                 torch.cuda.current_stream().wait_event(self.ev_tail[1])
                 torch.cuda.current_stream().synchronize()
