@@ -256,3 +256,59 @@ def format_detections(rows, image_shape):
         box[i] = [max(0, np.floor(x1).astype('int32')), max(0, np.floor(y1).astype('int32')),
                   min(image_shape[1], np.floor(x2).astype('int32')), min(image_shape[0], np.floor(y2).astype('int32'))]
     return box, conf, label
+
+
+def evaluate_map(dets, gts, num_classes, iou_thresholds):
+    """CPU restatement of the evaluator (yolo_continuous_b200/evaluate.py; the reference has no mAP code -- "parity
+    unpinned" for this component: the definition is the usual one, stated here).
+    dets: list over images of None | ndarray[n,7] (box[4], obj, class_conf, class) in the order NMS leaves them (class
+    ascending, score descending); gts: list over images of (boxes [m,4], labels [m]).  For every IoU threshold each
+    detection, in that order, takes the unmatched ground-truth box of its class with the highest IoU >= thr (ties: the
+    first); IoU = utils/bbox.py:62-72 in binary32.  AP per class = mean over the 101 recall points 0, .01, ... 1 of the
+    precision envelope (0 beyond the reached recall).  Returns (tp list over images of [T, n] uint8, ap [T, nc] float64
+    with NaN for classes without ground truth)."""
+    T = len(iou_thresholds)
+    tps, scores, classes = [], [], []
+    n_gt = np.zeros(num_classes, np.int64)
+    for det, (gb, gl) in zip(dets, gts):
+        gb, gl = np.asarray(gb, np.float32).reshape(-1, 4), np.asarray(gl).reshape(-1)
+        for c in gl:
+            n_gt[int(c)] += 1
+        if det is None or len(det) == 0:
+            tps.append(np.zeros((T, 0), np.uint8))
+            continue
+        iou = box_iou(np.ascontiguousarray(det[:, :4], np.float32), gb) if len(gb) else np.zeros((len(det), 0), np.float32)
+        tp = np.zeros((T, len(det)), np.uint8)
+        for t, thr in enumerate(iou_thresholds):
+            taken = np.zeros(len(gb), bool)
+            for d in range(len(det)):
+                best, bi = -1.0, -1
+                for g in range(len(gb)):
+                    if int(gl[g]) != int(det[d, 6]) or taken[g]:
+                        continue
+                    v = iou[d, g]
+                    if v >= np.float32(thr) and v > best:
+                        best, bi = v, g
+                if bi >= 0:
+                    taken[bi] = True
+                    tp[t, d] = 1
+        tps.append(tp)
+        scores.append((det[:, 4] * det[:, 5]).astype(np.float32))
+        classes.append(det[:, 6].astype(np.int64))
+    ap = np.full((T, num_classes), np.nan)
+    ap[:, n_gt > 0] = 0.0
+    if scores:
+        score, cls, tp = np.concatenate(scores), np.concatenate(classes), np.concatenate([t for t in tps if t.shape[1]], 1)
+        rec_thr = np.linspace(0, 1, 101)
+        for c in range(num_classes):
+            m = np.nonzero(cls == c)[0]
+            if n_gt[c] == 0 or len(m) == 0:
+                continue
+            o = m[np.argsort(-score[m], kind="stable")]
+            for t in range(T):
+                ctp = np.cumsum(tp[t, o].astype(np.float64))
+                recall, prec = ctp / n_gt[c], ctp / np.arange(1, len(o) + 1)
+                env = np.maximum.accumulate(prec[::-1])[::-1]
+                idx = np.searchsorted(recall, rec_thr, side="left")
+                ap[t, c] = np.where(idx < len(o), env[np.minimum(idx, len(o) - 1)], 0.0).mean()
+    return tps, ap

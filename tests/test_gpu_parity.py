@@ -1099,3 +1099,50 @@ def test_channels_last_maps_feed_the_head_k_major():
     with pytest.raises(_lib.YcError):
         PostBackbone(head, bs, shapes, torch.bfloat16, (320, 320), (240, 320), True, 0.25, 0.45, DEV, channels_last=True) \
             .run_device(nchw)
+
+
+def test_evaluator_on_device_vs_oracle():
+    """Batched on-device evaluator (yc_match_detections + the precision / recall integration on device tensors) against its
+    CPU restatement, fed by the pipeline's own output at mAP-eval thresholds."""
+    from yolo_continuous_b200.evaluate import DetectionEvaluator
+    from yolo_continuous_b200.pipeline import PostBackbone
+    ch, shapes, bs, nc = (64, 128, 256), [(40, 40), (20, 20), (12, 12)], 6, 80
+    head = _bench_like_head(nc, ch, 3).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(23)
+    thrs = [0.5, 0.75, 0.9]
+    ev = DetectionEvaluator(nc, thrs, DEV)
+    rng = np.random.default_rng(5)
+    all_det, all_gt = [], []
+    for step in range(2):
+        xs = [torch.randn(bs, c, h, w, generator=g, device=DEV).to(torch.bfloat16) for c, (h, w) in zip(ch, shapes)]
+        pipe = PostBackbone(head, bs, shapes, torch.bfloat16, (320, 320), (240, 320), True, 0.05, 0.65, DEV, use_graph=False)
+        rows, idx, counts, offsets = pipe.run_device(xs)
+        off = offsets.cpu().numpy()
+        host = rows[:off[-1]].cpu().numpy()
+        gtb, gtl, goff = [], [], [0]
+        for b in range(bs):
+            det = host[off[b]:off[b + 1]]
+            all_det.append(det if len(det) else None)
+            # ground truth: jittered copies of a few detections (so that matches exist at every threshold), a duplicate
+            # class/box pair, and boxes nothing detects; the last image of the first batch has none
+            n_pick = 0 if (step == 0 and b == bs - 1) or len(det) == 0 else min(12, len(det))
+            pick = rng.choice(len(det), n_pick, replace=False) if n_pick else np.zeros(0, np.int64)
+            boxes = det[pick, :4] + rng.normal(0, 1.0, (n_pick, 4)).astype(np.float32)
+            labels = det[pick, 6].astype(np.int64)
+            if n_pick:
+                boxes = np.concatenate([boxes, boxes[:1], np.float32([[1, 1, 5, 5]])])
+                labels = np.concatenate([labels, labels[:1], [7]])
+            gtb.append(boxes.astype(np.float32).reshape(-1, 4)); gtl.append(labels)
+            goff.append(goff[-1] + len(labels))
+            all_gt.append((gtb[-1], gtl[-1]))
+        ev.update(rows, offsets, torch.from_numpy(np.concatenate(gtb)), torch.from_numpy(np.concatenate(gtl)),
+                  torch.tensor(goff, dtype=torch.int32))
+    res = ev.compute()
+    tps, ap = orc.evaluate_map(all_det, all_gt, nc, thrs)
+    got_tp = torch.cat(ev._tp, 1).cpu().numpy()
+    assert np.array_equal(got_tp, np.concatenate([t for t in tps if t.shape[1]], 1))
+    assert got_tp.sum() > 20
+    got_ap = res["ap"].cpu().numpy()
+    assert np.array_equal(np.isnan(got_ap), np.isnan(ap))
+    np.testing.assert_allclose(np.nan_to_num(got_ap), np.nan_to_num(ap), rtol=0, atol=1e-12)
+    assert abs(float(res["map_50_95"]) - np.nanmean(ap, 1).mean()) < 1e-12

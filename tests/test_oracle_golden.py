@@ -182,3 +182,15 @@ def test_oracle_nms_matches_torchvision_on_random_boxes():
         want = tv.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr).numpy()
         got = orc.nms(boxes, scores, thr)
         assert np.array_equal(got, want), (n, thr)
+
+
+def test_oracle_evaluator_hand_computed_case():
+    """evaluate_map on a case small enough to do by hand: one class, two ground-truth boxes, three detections
+    (hit, duplicate of the same box = false positive, hit): AP@0.5 = mean over recall points of the envelope."""
+    gt = (np.array([[0, 0, 10, 10], [20, 20, 30, 30]], np.float32), np.array([0, 0]))
+    det = np.array([[0, 0, 10, 10, 1.0, 0.9, 0], [0, 0, 10, 9, 1.0, 0.8, 0], [20, 20, 30, 31, 1.0, 0.7, 0]], np.float32)
+    tps, ap = orc.evaluate_map([det], [gt], 2, [0.5, 0.95])
+    assert tps[0].tolist() == [[1, 0, 1], [1, 0, 0]]
+    # thr 0.5: precision 1, 1/2, 2/3 at recall .5, .5, 1 -> envelope 1 up to recall .5 (51 points), 2/3 beyond (50 points)
+    assert abs(ap[0, 0] - (51 * 1.0 + 50 * 2 / 3) / 101) < 1e-12
+    assert abs(ap[1, 0] - 51 / 101) < 1e-12 and np.isnan(ap[:, 1]).all()
