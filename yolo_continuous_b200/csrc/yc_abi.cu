@@ -209,8 +209,9 @@ static int fused_setup(const yc_head_desc *d, const yc_nms_params *p, void *work
     const int vrc = validate_head(d, false, row_off, rows_total);
     if (vrc != YC_OK) return vrc;
     YC_REQUIRE(p && workspace, YC_ERR_INVALID, "yc_detect_fused: null argument");
-    YC_REQUIRE(d->kind == YC_HEAD_IDETECT, YC_ERR_UNSUPPORTED, "yc_detect_fused: IDetect-style decode only");
-    YC_REQUIRE(p->bs == d->bs && p->rows == *rows_total && p->nc == d->no - 5 && p->nc > 0, YC_ERR_INVALID,
+    YC_REQUIRE(d->kind == YC_HEAD_IDETECT || d->kind == YC_HEAD_IBIN, YC_ERR_UNSUPPORTED, "yc_detect_fused: IDetect / IBin decode only");
+    const int nc_head = d->kind == YC_HEAD_IBIN ? d->no - 2 * (d->bin_count + 1) - 3 : d->no - 5;
+    YC_REQUIRE(p->bs == d->bs && p->rows == *rows_total && p->nc == nc_head && p->nc > 0, YC_ERR_INVALID,
                "yc_detect_fused: nms params (bs=%d rows=%d nc=%d) do not match the head (bs=%d rows=%d no=%d)", p->bs,
                p->rows, p->nc, d->bs, *rows_total, d->no);
     YC_REQUIRE(!p->correct_boxes || p->image_hw, YC_ERR_INVALID, "yc_detect_fused: correct_boxes needs image_hw");

@@ -207,7 +207,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
             // fused mode: the (scale, bias) pairs this warp needs live in registers; they change with the level and,
             // when the anchors of a pixel block are separate tiles (na*no > 256 columns), with the anchor group
-            if (P.fused && tc.lv * YC_MAX_ANCHORS + tc.g != cur_key) {
+            if (P.fused && !P.ibin && tc.lv * YC_MAX_ANCHORS + tc.g != cur_key) {
                 sbv = load_box_sb(sb, lane, P.nc);
                 cur_key = tc.lv * YC_MAX_ANCHORS + tc.g;
             }
@@ -220,7 +220,8 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 continue;
             }
             if (P.fused) {
-                fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane, sbv);
+                if (P.ibin) fused_epilogue_ibin(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane);
+                else fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane, sbv);
                 continue;
             }
             store_epilogue<false>(P, L, tc.b, tc.p0, tc.g, e, q, lane, tmem_base + (uint32_t)(buf * TC_MAX_N), (uint8_t *)slabs,
@@ -280,7 +281,6 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     const int npad = round_up(na_tile * d->no, 16);
     const int npad_total = round_up(N, 16);
     YC_REQUIRE(!(fused && d->x_dtype != YC_BF16), YC_ERR_UNSUPPORTED, "tcgen05 head: the fused step takes bf16 feature maps");
-    YC_REQUIRE(!(fused && ibin), YC_ERR_UNSUPPORTED, "tcgen05 head: the fused step supports IDetect-style decode only");
     EncodeTiledFn enc = encode_tiled();
     YC_REQUIRE(enc != nullptr, YC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (!g_num_sms) {
@@ -303,7 +303,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     const uint32_t slab_bytes = fused ? (uint32_t)round_up(TC_QUEUE_ROWS * (d->no - 5) * 4, 16)
                                 : ibin ? (uint32_t)round_up(32 * no_out * 4 + (any_raw ? 32 * d->no * 4 : 0), 16)
                                        : (uint32_t)round_up(32 * d->no * 4, 16);
-    const int epi_warps = ibin ? 12 : 4 * na_tile;
+    const int epi_warps = ibin ? (fused ? 4 : 12) : 4 * na_tile;   // fused IBin: one warp per quadrant (most rows stop at the objectness)
     // K=64 per stage: 4 stages in the fused mode (no z slabs in shared memory), 2 next to the slabs.
     // (K=128 x 2 stages measured 6 us slower on the C2 batch; YC_TC_BK overrides for experiments.)
     int bk = 64;
@@ -316,7 +316,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     const int tile_px = pair ? 2 * TC_BM : TC_BM;
     const uint32_t b_slot_bytes = (uint32_t)round_up(npad * 64 * 2, 1024);   // npad is a multiple of 16: 2 KB steps
     const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * b_slot_bytes;
-    const size_t fixed = 1024 + (size_t)(ibin ? 4 : 4 * na_tile) * slab_bytes + 256;
+    const size_t fixed = 1024 + (size_t)(ibin ? 4 : 4 * na_tile) * slab_bytes + 256;   // (fused IBin: 4 warps x one area each)
     int stages = TC_MAX_STAGES;
     while (stages > 2 && fixed + (size_t)stages * stage_bytes > 227 * 1024) --stages;
     const size_t smem_bytes = fixed + (size_t)stages * stage_bytes;

@@ -304,7 +304,8 @@ __device__ __forceinline__ void epi_range_raw(uint32_t taddr, int cb, int ce, co
 // ---- fused epilogue (S3): class max / threshold / candidate emission straight from TMEM -----------------
 // logits of W consecutive class columns starting at accumulator column c (class index c - 5)
 template <int W, bool EXACT>
-__device__ __forceinline__ void cls_chunk(uint32_t taddr, int c, const float2 *__restrict__ sb, float &bestv, int &besti)
+__device__ __forceinline__ void cls_chunk(uint32_t taddr, int c, const float2 *__restrict__ sb, float &bestv, int &besti,
+                                          int cbase = 5)
 {
     uint32_t v[W];
     TmemLd<W>::ld(taddr + (uint32_t)c, v);
@@ -315,23 +316,25 @@ __device__ __forceinline__ void cls_chunk(uint32_t taddr, int c, const float2 *_
         float t = fmaf(__uint_as_float(v[j]), s_b.x, s_b.y);
         if (EXACT) {
             t = sigmoidf_fast(t); // compare what z would hold (first maximum of the sigmoids, torch.max)
-            if (t > bestv) { bestv = t; besti = c + j - 5; }
+            if (t > bestv) { bestv = t; besti = c + j - cbase; }
         } else {
             bestv = fmaxf(bestv, t); // quick pass: only the largest class logit is needed
         }
     }
 }
 
+// classes live in the accumulator columns [cbase, no) (IDetect: 5; IBin: behind the two bin blocks and the objectness)
 template <bool EXACT>
-__device__ __forceinline__ void cls_scan(uint32_t taddr, int no, const float2 *__restrict__ sb, float &bestv, int &besti)
+__device__ __forceinline__ void cls_scan(uint32_t taddr, int no, const float2 *__restrict__ sb, float &bestv, int &besti,
+                                         int cbase = 5)
 {
-    int c = 5;
-    for (; c + 16 <= no; c += 16) cls_chunk<16, EXACT>(taddr, c, sb, bestv, besti);
+    int c = cbase;
+    for (; c + 16 <= no; c += 16) cls_chunk<16, EXACT>(taddr, c, sb, bestv, besti, cbase);
     const int rem = no - c;
-    if (rem & 8) { cls_chunk<8, EXACT>(taddr, c, sb, bestv, besti); c += 8; }
-    if (rem & 4) { cls_chunk<4, EXACT>(taddr, c, sb, bestv, besti); c += 4; }
-    if (rem & 2) { cls_chunk<2, EXACT>(taddr, c, sb, bestv, besti); c += 2; }
-    if (rem & 1) { cls_chunk<1, EXACT>(taddr, c, sb, bestv, besti); }
+    if (rem & 8) { cls_chunk<8, EXACT>(taddr, c, sb, bestv, besti, cbase); c += 8; }
+    if (rem & 4) { cls_chunk<4, EXACT>(taddr, c, sb, bestv, besti, cbase); c += 4; }
+    if (rem & 2) { cls_chunk<2, EXACT>(taddr, c, sb, bestv, besti, cbase); c += 2; }
+    if (rem & 1) { cls_chunk<1, EXACT>(taddr, c, sb, bestv, besti, cbase); }
 }
 
 
@@ -652,5 +655,42 @@ __device__ __forceinline__ void fused_epilogue(const TcParams &P, const TcLevel 
             else mbar_arrive(tempty);
         }
 }
+
+// Fused epilogue for the IBin head (nets/ibin.py:56-74 + detect.py:108-121 in one pass; one anchor per tile, one warp per
+// TMEM lane quadrant): reject on the objectness column alone (it sits behind the two bin blocks); only a warp that holds a
+// survivor reads the rest of its rows -- class scores (first maximum of the sigmoids, as the z path sees them), then the
+// 2 + 2 * (bin_count + 1) box columns through the same decode as the z-writing epilogue (bin arg-max on the sigmoids)
+// -- and emits NMS candidates.  The 127-sigmoid row decode therefore runs for the few warps with a survivor instead of for
+// every row, and z is never written.  `scratch`: 4 floats per lane of this warp's shared-memory area.
+__device__ __forceinline__ void fused_epilogue_ibin(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar,
+                                                    uint32_t taddr, float *scratch, uint64_t *tempty, int lane)
+{
+    const int no = P.no, len = P.bin_count + 1, c_obj = 2 + 2 * len, c_cls = c_obj + 1;
+    const int p = prow0 + lane;
+    const float2 *sb = L.sb + ar * no;
+    uint32_t v1[1];
+    TmemLd<1>::ld(taddr + (uint32_t)c_obj, v1);
+    tmem_ld_wait();
+    const float2 so = __ldg(sb + c_obj);
+    const float obj = sigmoidf_fast(fmaf(__uint_as_float(v1[0]), so.x, so.y));
+    bool pass = lane < nv && obj >= P.conf;    // class scores are sigmoids (<= 1): obj >= conf is necessary
+    if (__ballot_sync(0xffffffffu, pass)) {
+        float bv = -1.0f;
+        int best = 0;
+        cls_scan<true>(taddr, no, sb, bv, best, c_cls);
+        const float score = __fmul_rn(obj, bv);
+        pass = pass && score >= P.conf;
+        float *srow = scratch + lane * 4;
+        epi_range_ibin<false>(taddr, 0, c_obj, true, true, sb, srow, (float)(p % L.nx), (float)(p / L.nx), L.stride, L.stride_y,
+                              L.anchor_wh[2 * ar], L.anchor_wh[2 * ar + 1], P);
+        float x1, y1, x2, y2;
+        xywh_to_corners(srow[0], srow[1], srow[2], srow[3], P.div_w, P.div_h, x1, y1, x2, y2);
+        emit_candidates(pass, b, L.row_off + ar * L.HW + p, P.rows_total, P.nc, x1, y1, x2, y2, obj, bv, score, best, P.ws);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty);
+}
+
 
 } // namespace yc

@@ -33,8 +33,10 @@ class PostBackbone:
         self.channels_last = bool(channels_last)
         if self.channels_last and dtype != torch.bfloat16:
             raise _lib.YcError("channels_last=True needs bfloat16 feature maps")
-        if not hasattr(head, "m") or head.no != head.nc + 5:
-            raise _lib.YcError("PostBackbone drives IDetect/IAuxDetect-style heads (no = nc + 5)")
+        # IDetect / IAuxDetect (no = nc + 5) and IBin (no = nc + 3 + 2 * (bin_count + 1): nets/ibin.py:20-21)
+        self.ibin = hasattr(head, "w_bin_sigmoid")
+        if not hasattr(head, "m") or head.no != head.nc + (3 + 2 * (head.bin_count + 1) if self.ibin else 5):
+            raise _lib.YcError("PostBackbone drives IDetect / IAuxDetect / IBin heads")
         self.nl = len(self.shapes)
         dev = self.device
         self.rows = sum(self.na * h * w for h, w in self.shapes)
@@ -43,7 +45,8 @@ class PostBackbone:
             fmt = torch.channels_last if self.channels_last else torch.contiguous_format
             self.x_dev = [torch.empty((bs, c, h, w), dtype=dtype, device=dev, memory_format=fmt)
                           for c, (h, w) in zip(self.ch, self.shapes)]
-            self.z = torch.empty((bs, self.rows, self.no), dtype=torch.float32, device=dev)
+            self.no_out = self.nc + 5      # columns of a z row (IBin re-packs its 127 outputs to nc + 5, nets/ibin.py:72)
+            self.z = torch.empty((bs, self.rows, self.no_out), dtype=torch.float32, device=dev)
             # Output message(s): [counts (bs) | offsets (bs+1) | pad] int32 header followed by the detection rows
             # [bs*rows, 7] fp32 in ONE allocation, so that a fixed-size prefix (header + the first `gather_rows`
             # rows) can be sent as a single all-gather / D2H copy.  Two of them when double-buffered (the
@@ -72,7 +75,10 @@ class PostBackbone:
                 if bs * self.rows <= (1 << 22) else torch.empty((1 << 22, 7), dtype=torch.float32).pin_memory()
         # descriptors (pointers filled per call for the head inputs)
         d = _lib.HeadDesc()
-        d.kind, d.path = _lib.YC_HEAD_IDETECT, head.head_path
+        d.kind, d.path = (_lib.YC_HEAD_IBIN if self.ibin else _lib.YC_HEAD_IDETECT), head.head_path
+        if self.ibin:
+            self._bins = head.w_bin_sigmoid.bins.to(device=dev, dtype=torch.float32).contiguous()
+            d.bin_count, d.bins = head.bin_count, self._bins.data_ptr()
         d.x_dtype = _lib.YC_BF16 if dtype == torch.bfloat16 else _lib.YC_F32
         d.nl, d.na, d.no, d.bs = self.nl, self.na, self.no, bs
         d.x_channels_last = 1 if self.channels_last else 0
@@ -89,7 +95,7 @@ class PostBackbone:
         self.desc = d
         self._weight_key = self._weights_version()
         p = _lib.NmsParams()
-        p.bs, p.rows, p.row_stride, p.nc = bs, self.rows, self.no, self.nc
+        p.bs, p.rows, p.row_stride, p.nc = bs, self.rows, self.no_out, self.nc
         p.conf_thres, p.nms_thres = float(conf_thres), float(nms_thres)
         p.write_corners, p.correct_boxes, p.letterbox = 0, 1, 1 if letterbox_image else 0
         p.input_h, p.input_w = int(input_shape[0]), int(input_shape[1])
