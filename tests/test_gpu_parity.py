@@ -806,6 +806,38 @@ def _near_threshold_pairs(z_norm, nc, conf, iou, band):
     return n_sc, n_iou
 
 
+def _oracle_params_folded(head, kind):
+    """Oracle parameters for bf16 feature maps that describe exactly what the product computes: the MMA multiplies the
+    bf16-rounded weights with x, while ImplicitA is folded into the bias with the FLOAT32 weights (b' = b + W.ia, binary64
+    accumulation, yc_head_pack).  (_oracle_params(..., bf16=True) rounds the weights in the ia term too, which differs by
+    (W - bf16(W)).ia: invisible for N(0,.02) weights, ~2e-4 on a logit for heads with large class-row weights.)"""
+    p = _oracle_params(head, kind, True)
+    for i in range(head.nl):
+        w32 = head.m[i].weight.detach()[:, :, 0, 0].double()
+        ia = head.ia[i].implicit.detach().reshape(-1).double()
+        p["b"][i] = (head.m[i].bias.detach().double() + w32 @ ia).float().numpy()
+        p["ia"][i] = np.zeros_like(p["ia"][i])
+    return p
+
+
+def _assert_same_detections(got_idx, got_rows, want_idx, want_rows, what, score_band=1e-4, box_atol=0.05):
+    """Kept set, classes and values equal; the ORDER (class ascending, score descending) may differ from the oracle's
+    only between neighbours whose oracle scores are closer than `score_band` (the two sides see inputs that differ by
+    the tensor core's accumulation noise, so a near-tie within a class may legitimately swap)."""
+    assert np.array_equal(np.sort(got_idx), np.sort(want_idx)), what
+    pos = {int(r): i for i, r in enumerate(want_idx)}
+    perm = np.array([pos[int(r)] for r in got_idx], np.int64)
+    w = want_rows[perm]
+    assert np.array_equal(got_rows[:, 6], w[:, 6]), what
+    np.testing.assert_allclose(got_rows[:, 4:6], w[:, 4:6], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(got_rows[:, :4], w[:, :4], rtol=1e-3, atol=box_atol)
+    moved = np.nonzero(perm != np.arange(len(perm)))[0]
+    ws = want_rows[:, 4] * want_rows[:, 5]
+    for i in moved:
+        assert want_rows[perm[i], 6] == want_rows[i, 6] and abs(ws[perm[i]] - ws[i]) < score_band, (what, int(i))
+    return len(moved)
+
+
 C2_CH, C2_SHAPES = (256, 512, 1024), [(80, 80), (40, 40), (20, 20)]
 
 
@@ -820,7 +852,7 @@ def test_fused_pair_kernel_vs_oracle_c2_shapes():
     head = _bench_like_head(nc, C2_CH, 12)
     g = torch.Generator().manual_seed(34)
     xs = [torch.randn(bs, c, h, w, generator=g).to(torch.bfloat16) for c, (h, w) in zip(C2_CH, C2_SHAPES)]
-    p = _oracle_params(head, "idetect", True)
+    p = _oracle_params_folded(head, "idetect")
     z_ref, raw_ref = orc.head_forward("idetect", p, [x.float().numpy() for x in xs], [8.0, 16.0, 32.0])
     zn = z_ref.copy()
     zn[..., :4] /= np.float32(640.0)
@@ -843,12 +875,8 @@ def test_fused_pair_kernel_vs_oracle_c2_shapes():
     scale = box_scale(p["anchors"], [8.0, 16.0, 32.0], C2_SHAPES, head.na, 85)
     assert_close_scaled(z.cpu().numpy(), z_ref, scale, RTOL_BF16, "tcgen05 forward @ C2 shapes")
     assert_close_scaled(z.cpu().numpy(), z_ref, scale, 1e-4, "tcgen05 forward @ C2 shapes (tight)")
-    for i in range(3):
-        # raw logits at the bf16 tolerance |a-b| <= 1e-3 * max(|ref|, 1).  (The oracle multiplies the bf16-rounded
-        # weights with x + ia; the product folds ia into the bias with the float32 weights: with the large class-row
-        # weights of this head the two differ by up to ~2e-4 on a logit, far above the accumulation noise.)
-        r, want_r = raws[i].cpu().numpy(), raw_ref[i]
-        assert np.all(np.abs(r - want_r) <= RTOL_BF16 * np.maximum(np.abs(want_r), 1.0)), float(np.abs(r - want_r).max())
+    for i in range(3):   # class logits reach |t| ~ 10: the accumulation noise is relative
+        np.testing.assert_allclose(raws[i].cpu().numpy(), raw_ref[i], rtol=1e-4, atol=1e-4)
     # (2) fused step: CTA-pair kernel (default) and the 1-CTA kernel (YC_TC_2CTA=0), eager and pipelined graphs
     import os
     for two_cta in ("1", "0"):
@@ -871,11 +899,8 @@ def test_fused_pair_kernel_vs_oracle_c2_shapes():
         for rows, idx, counts, offsets in res:
             off = offsets.cpu().numpy()
             for b in range(bs):
-                assert np.array_equal(idx[off[b]:off[b + 1]].cpu().numpy(), widx[b]), (two_cta, b)
-                got = rows[off[b]:off[b + 1]].cpu().numpy()
-                assert np.array_equal(got[:, 6], want[b][:, 6])
-                np.testing.assert_allclose(got[:, 4:6], want[b][:, 4:6], rtol=1e-3, atol=1e-5)
-                np.testing.assert_allclose(got[:, :4], want[b][:, :4], rtol=1e-3, atol=0.05)   # image pixels
+                _assert_same_detections(idx[off[b]:off[b + 1]].cpu().numpy(), rows[off[b]:off[b + 1]].cpu().numpy(), widx[b],
+                                        want[b], (two_cta, b))
 
 
 def test_fused_pair_kernel_resident_levels_back_to_back():
@@ -1210,12 +1235,12 @@ def test_ibin_fused_step_vs_oracle_pipeline():
     head = _ibin_head(ch, 9)
     g = torch.Generator().manual_seed(10)
     xs = [torch.randn(bs, c, h, w, generator=g).to(torch.bfloat16) for c, (h, w) in zip(ch, shapes)]
-    p = _oracle_params(head, "ibin", True)
+    p = _oracle_params_folded(head, "ibin")
     z_ref, _ = orc.head_forward("ibin", p, [x.float().numpy() for x in xs], [8.0, 16.0, 32.0])
     zn = z_ref.copy()
     zn[..., :4] /= np.float32(128.0)
     sc = np.sort((zn[..., 4] * zn[..., 5:].max(-1)).ravel())
-    sc = sc[(sc >= 0.15) & (sc <= 0.3)].astype(np.float64)
+    sc = sc[(sc >= 0.02) & (sc <= 0.05)].astype(np.float64)
     k = int(np.argmax(np.diff(sc)))
     conf = float(np.float32((sc[k] + sc[k + 1]) / 2))
     assert sc[k + 1] - sc[k] > 2e-4
