@@ -196,7 +196,8 @@ YC_API int yc_xchg_free(void *buf);
 YC_API int yc_xchg_push(const void *msg, int hdr_ints, int bs, int max_rows, void *const *peers_dev, int world, int rank,
                  int slots, size_t msg_bytes, yc_stream_t stream);
 /* lag: the kernel returns at once unless this rank has itself pushed message (next wait sequence number + lag) already;
- * "push(i); wait(lag = 1)" per step waits for step i - 1 and never spins in the steady state; lag = 0 waits for the latest. */
+ * "push(i); wait(lag = 1)" per step waits for step i - 1 and never spins in the steady state; lag = 0 waits for the next
+ * message; lag = -1 waits for every message this rank has pushed so far (end of a stream of batches). */
 YC_API int yc_xchg_wait(void *const *peers_dev, int world, int rank, int slots, size_t msg_bytes, int lag, yc_stream_t stream);
 /* out4 (host): next push sequence number, next wait sequence number, internal, error (1 = a wait timed out). Synchronises. */
 YC_API int yc_xchg_state(const void *buf, int world, int slots, size_t msg_bytes, uint32_t *out4, yc_stream_t stream);

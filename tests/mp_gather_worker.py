@@ -77,7 +77,7 @@ def main():
     # ---- the repo's own exchange: push / wait kernels over NVLink peer memory, inside the per-step graphs ------------
     from yolo_continuous_b200.parallel import PeerExchange
     for gather_rows in (4096, 8):
-        xc = PeerExchange(pipe.hdr_ints, bs, gather_rows, dev, slots=4)
+        xc = PeerExchange(pipe.hdr_ints, bs, gather_rows, dev, slots=4 if gather_rows == 8 else 8)
         pipe.attach_exchange(xc)
         n_rounds = 3                   # 15 messages: every slot is reused three times (credits / acknowledgements)
         for rnd in range(n_rounds):
@@ -86,7 +86,7 @@ def main():
                 if rank == 1 and s == 2:
                     torch.cuda._sleep(20_000_000)    # one rank falls behind: the others must wait, not overwrite
         pipe.drain()
-        xc.wait()
+        xc.wait_all()
         sp, sw, err = xc.state()
         assert (sp, sw, err) == (n_rounds * n_steps, n_rounds * n_steps, 0), (sp, sw, err)
         # the last `slots` messages are still in the receive buffer: sequence number q holds step q % n_steps

@@ -22,7 +22,11 @@ struct XchgState {             // local to a rank (lives behind its receive buff
     unsigned int seq_wait;     // sequence number of the next message set this rank waits for
     unsigned int done;         // CTAs of the running push kernel that have finished
     unsigned int error;        // sticky: 1 = a wait timed out
+    unsigned int peer_done[60]; // CTAs of the running push kernel that have finished their part for peer p
 };
+constexpr int XCHG_MAX_WORLD = 60;
+constexpr int XCHG_SPLIT = 4;  // CTAs per peer in the push kernel
+constexpr int XCHG_UNROLL = 8; // 16-byte loads in flight per thread: 4 CTAs x 256 threads x 8 x 16 B = 128 KB per peer
 
 struct XchgLayout {
     size_t flags_off, acks_off, state_off, total;
@@ -58,13 +62,17 @@ __device__ __forceinline__ unsigned long long global_ns()
 
 constexpr unsigned long long XCHG_TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;
 
-// grid = world CTAs: CTA p copies this rank's message into peer p's slot and raises the flag there.
+// grid = world x XCHG_SPLIT CTAs: the CTAs of peer p copy this rank's message into peer p's slot; the last of them raises
+// the flag there.
+// 256 threads x <= 48 registers: like the NMS kernels, a CTA must fit NEXT TO a resident head CTA (512 threads x 96
+// registers, 213 KB of shared memory) -- the push of step i runs while the persistent head kernel of step i + 1 holds
+// every SM; a CTA that does not fit would wait for that kernel to end and stall the pipeline by a step.
 // msg: [hdr_ints int32: counts (bs) | offsets (bs + 1) | pad][rows: 7 floats each]; only the rows that exist (and fit) move.
-__global__ void __launch_bounds__(512) xchg_push_kernel(const uint8_t *__restrict__ msg, int hdr_ints, int bs, int max_rows,
+__global__ void __maxnreg__(48) xchg_push_kernel(const uint8_t *__restrict__ msg, int hdr_ints, int bs, int max_rows,
                                                         uint8_t *const *__restrict__ peers, int world, int rank, int slots,
                                                         size_t msg_bytes, XchgLayout lay)
 {
-    const int p = blockIdx.x;
+    const int p = blockIdx.x / XCHG_SPLIT, part = blockIdx.x % XCHG_SPLIT;
     uint8_t *mine = peers[rank];
     XchgState *st = (XchgState *)(mine + lay.state_off);
     __shared__ unsigned int s_q;
@@ -85,17 +93,33 @@ __global__ void __launch_bounds__(512) xchg_push_kernel(const uint8_t *__restric
     const unsigned int q = s_q;
     const int slot = (int)(q % (unsigned)slots);
     const int total = ((const int *)msg)[2 * bs];
-    const size_t bytes = ((size_t)hdr_ints * 4 + (size_t)min(total, max_rows) * 28 + 15) / 16 * 16;
+    const size_t n16 = ((size_t)hdr_ints * 4 + (size_t)min(total, max_rows) * 28 + 15) / 16;
     uint8_t *dst = peers[p] + ((size_t)slot * world + rank) * msg_bytes;
     const uint4 *s4 = (const uint4 *)msg;
     uint4 *d4 = (uint4 *)dst;
-    for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d4[i] = s4[i];
-    __threadfence_system();
+    // next to a head kernel that saturates HBM a dependent load -> store round trip takes microseconds: all loads of a
+    // thread are issued before its first store (the grid is sized so that XCHG_UNROLL iterations cover a full message)
+    const size_t lo = n16 * part / XCHG_SPLIT, hi = n16 * (part + 1) / XCHG_SPLIT;
+    for (size_t i0 = lo + threadIdx.x; i0 < hi; i0 += (size_t)blockDim.x * XCHG_UNROLL) {
+        uint4 v[XCHG_UNROLL];
+#pragma unroll
+        for (int u = 0; u < XCHG_UNROLL; ++u)
+            if (i0 + (size_t)u * blockDim.x < hi) v[u] = __ldcs(s4 + i0 + (size_t)u * blockDim.x);
+#pragma unroll
+        for (int u = 0; u < XCHG_UNROLL; ++u)
+            if (i0 + (size_t)u * blockDim.x < hi) d4[i0 + (size_t)u * blockDim.x] = v[u];
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        st_release_sys((unsigned int *)(peers[p] + lay.flags_off) + (size_t)slot * world + rank, q + 1u);
+        // ONE system-scope fence per CTA (after the barrier it orders the stores of all its threads): a fence per thread
+        // next to a head kernel with thousands of loads in flight cost ~20 us
+        __threadfence_system();
+        if (atomicAdd(&st->peer_done[p], 1u) == XCHG_SPLIT - 1) {   // all parts for this peer are on their way: raise the flag
+            st->peer_done[p] = 0u;
+            st_release_sys((unsigned int *)(peers[p] + lay.flags_off) + (size_t)slot * world + rank, q + 1u);
+        }
         __threadfence();
-        if (atomicAdd(&st->done, 1u) == (unsigned)world - 1u) {   // last CTA: the message is on its way everywhere
+        if (atomicAdd(&st->done, 1u) == (unsigned)(world * XCHG_SPLIT) - 1u) {   // last CTA of the kernel
             st->done = 0u;
             __threadfence();
             *(volatile unsigned int *)&st->seq_push = q + 1u;
@@ -112,20 +136,25 @@ __global__ void __launch_bounds__(32) xchg_wait_kernel(uint8_t *const *__restric
 {
     uint8_t *mine = peers[rank];
     XchgState *st = (XchgState *)(mine + lay.state_off);
-    const unsigned int j = *(volatile unsigned int *)&st->seq_wait;
-    if (*(volatile unsigned int *)&st->seq_push < j + 1u + (unsigned)lag) return;
-    const int slot = (int)(j % (unsigned)slots);
-    for (int r = threadIdx.x; r < world; r += 32) {
-        const unsigned int *flag = (const unsigned int *)(mine + lay.flags_off) + (size_t)slot * world + r;
-        const unsigned long long t0 = global_ns();
-        while ((int)(ld_acquire_sys(flag) - (j + 1u)) < 0) {
-            if (global_ns() - t0 > XCHG_TIMEOUT_NS) { atomicExch(&st->error, 1u); break; }
-            __nanosleep(200);
+    do {   // lag < 0: until every message this rank has pushed so far has been awaited
+        const unsigned int j = *(volatile unsigned int *)&st->seq_wait;
+        if (*(volatile unsigned int *)&st->seq_push < j + 1u + (unsigned)max(lag, 0)) return;
+        const int slot = (int)(j % (unsigned)slots);
+        for (int r = threadIdx.x; r < world; r += 32) {
+            const unsigned int *flag = (const unsigned int *)(mine + lay.flags_off) + (size_t)slot * world + r;
+            const unsigned long long t0 = global_ns();
+            while ((int)(ld_acquire_sys(flag) - (j + 1u)) < 0) {
+                if (global_ns() - t0 > XCHG_TIMEOUT_NS) { atomicExch(&st->error, 1u); break; }
+                __nanosleep(200);
+            }
+            // the acknowledgement orders nothing of this kernel's: what it declares consumed was read by earlier work of
+            // the stream, complete before this kernel started -- a plain (relaxed, system-scope) store
+            *(volatile unsigned int *)((unsigned int *)(peers[r] + lay.acks_off) + rank) = j;
         }
-        st_release_sys((unsigned int *)(peers[r] + lay.acks_off) + rank, j);
-    }
-    __syncwarp();
-    if (threadIdx.x == 0) *(volatile unsigned int *)&st->seq_wait = j + 1u;
+        __syncwarp();
+        if (threadIdx.x == 0) *(volatile unsigned int *)&st->seq_wait = j + 1u;
+        __syncwarp();
+    } while (lag < 0);
 }
 
 } // namespace yc
@@ -140,6 +169,8 @@ extern "C" size_t yc_xchg_bytes(int world, int slots, size_t msg_bytes)
 
 extern "C" int yc_xchg_alloc(int world, int slots, size_t msg_bytes, void **buf, uint8_t *handle64)
 {
+    static_assert(sizeof(XchgState) <= 256, "state block");
+    YC_REQUIRE(world <= XCHG_MAX_WORLD, YC_ERR_UNSUPPORTED, "yc_xchg_alloc: at most %d ranks", XCHG_MAX_WORLD);
     YC_REQUIRE(buf && handle64 && world > 0 && slots >= 2 && msg_bytes % 16 == 0 && msg_bytes > 0, YC_ERR_INVALID,
                "yc_xchg_alloc: bad argument (msg_bytes must be a multiple of 16, slots >= 2)");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -183,7 +214,7 @@ extern "C" int yc_xchg_push(const void *msg, int hdr_ints, int bs, int max_rows,
                YC_ERR_INVALID, "yc_xchg_push: bad argument");
     YC_REQUIRE((size_t)hdr_ints * 4 + (size_t)max_rows * 28 <= msg_bytes && (((uintptr_t)msg | msg_bytes) & 15) == 0, YC_ERR_INVALID,
                "yc_xchg_push: message does not fit msg_bytes / is not 16-byte aligned");
-    xchg_push_kernel<<<world, 512, 0, (cudaStream_t)stream>>>((const uint8_t *)msg, hdr_ints, bs, max_rows,
+    xchg_push_kernel<<<world * XCHG_SPLIT, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)msg, hdr_ints, bs, max_rows,
                                                                (uint8_t *const *)peers_dev, world, rank, slots, msg_bytes,
                                                                xchg_layout(world, slots, msg_bytes));
     YC_CUDA(cudaGetLastError());
@@ -193,7 +224,7 @@ extern "C" int yc_xchg_push(const void *msg, int hdr_ints, int bs, int max_rows,
 extern "C" int yc_xchg_wait(void *const *peers_dev, int world, int rank, int slots, size_t msg_bytes, int lag,
                             yc_stream_t stream)
 {
-    YC_REQUIRE(peers_dev && world > 0 && rank >= 0 && rank < world && slots >= 2 && lag >= 0 && lag < slots - 1, YC_ERR_INVALID,
+    YC_REQUIRE(peers_dev && world > 0 && rank >= 0 && rank < world && slots >= 2 && lag >= -1 && lag < slots - 1, YC_ERR_INVALID,
                "yc_xchg_wait: bad argument");
     xchg_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((uint8_t *const *)peers_dev, world, rank, slots, lag,
                                                          xchg_layout(world, slots, msg_bytes));

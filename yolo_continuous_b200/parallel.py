@@ -165,7 +165,7 @@ class PeerExchange:
     wait() for sequence number j declares every message before j consumed (their slots may be overwritten): read the
     views of `unpack()` before waiting `slots - 1` steps further."""
 
-    def __init__(self, hdr_ints, bs, gather_rows, device, group=None, slots=4):
+    def __init__(self, hdr_ints, bs, gather_rows, device, group=None, slots=8):
         import ctypes as C
 
         from . import _lib
@@ -212,6 +212,10 @@ class PeerExchange:
         s = self._C.c_void_p((stream or torch.cuda.current_stream(self.device)).cuda_stream)
         self._lib.check(self._lib.lib.yc_xchg_wait(self.peers.data_ptr(), self.world, self.rank, self.slots, self.msg_bytes,
                                                    int(lag), s), "yc_xchg_wait")
+
+    def wait_all(self, stream=None):
+        """Enqueue the wait for every message this rank has pushed so far (end of a stream of batches)."""
+        self.wait(stream, lag=-1)
 
     def state(self):
         """(next push seq, next wait seq, error) read back from the device (synchronises the current stream)."""

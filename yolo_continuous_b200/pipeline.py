@@ -112,7 +112,8 @@ class PostBackbone:
         self._graphs = {}
         self._pgraphs = {}
         self._in_flight = False
-        self.exchange = None
+        self._n_sub = 0
+        self.exchange, self.xchg_stream = None, None
         self._eager_dirty = False
         self._hp = None
         self.use_graph = use_graph and not self.overlap
@@ -228,8 +229,20 @@ class PostBackbone:
                 _lib.check(_lib.lib.yc_nms_workspace_reset(C.byref(self.nms_params), self.ws.data_ptr(), self.ws.numel(),
                                                            C.c_void_p(tail.cuda_stream)), "yc_nms_workspace_reset")
                 if self.exchange is not None:
-                    self.exchange.push(self.msgs[c], tail)
-                    self.exchange.wait(tail, lag=1)
+                    import os
+                    dbg = int(os.environ.get("YC_XCHG_DEBUG", "0"))
+                    tev = getattr(self, "_xchg_events", None)     # timing experiments (tools/xchg_time.py)
+                    if tev is not None:
+                        tev.append([torch.cuda.Event(enable_timing=True) for _ in range(3)])
+                        tev[-1][0].record(tail)
+                    if dbg < 2:
+                        self.exchange.push(self.msgs[c], tail)
+                    if tev is not None:
+                        tev[-1][1].record(tail)
+                    if dbg < 1:
+                        self.exchange.wait(tail, lag=1)
+                    if tev is not None:
+                        tev[-1][2].record(tail)
                 self.ev_tail[c].record(tail)
                 self._eager_dirty = True
             return
@@ -309,8 +322,13 @@ class PostBackbone:
                     self._check(i, x)
                 self._pipelined_step(features, c, with_tail=False)
                 self._in_flight = True
+                self._n_sub = 1
                 return None
-            key = tuple(x.data_ptr() for x in features) + (c,)
+            self._n_sub += 1
+            # multi-GPU: from the third batch on the graph has a third branch that pushes the results of the batch before
+            # the previous one (complete since the previous graph) to all ranks and awaits earlier messages
+            with_push = self.exchange is not None and self._n_sub >= 3
+            key = tuple(x.data_ptr() for x in features) + (c, with_push)
             g = self._pgraphs.get(key)
             if g is None:
                 for i, x in enumerate(features):
@@ -320,7 +338,7 @@ class PostBackbone:
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
-                    self._pipelined_step(features, c)
+                    self._pipelined_step(features, c, with_push=with_push)
                 if len(self._pgraphs) > 16:
                     self._pgraphs.clear()
                 self._pgraphs[key] = g
@@ -329,12 +347,19 @@ class PostBackbone:
         return None if prev is None else self._views(prev)
 
     def drain(self):
-        """NMS kernels of the last submitted batch (eager); returns its result views, complete on the current stream."""
+        """NMS kernels of the last submitted batch (eager); returns its result views, complete on the current stream.
+        With an exchange attached the batches not pushed yet (the last two) are pushed, in order; follow with
+        `exchange.wait_all()` to have every rank's messages."""
         if not self._in_flight:
             return None
         with torch.cuda.device(self.device):
             c = self.cur
-            self._tail(c, torch.cuda.current_stream())
+            s = torch.cuda.current_stream()
+            self._tail(c, s)
+            if self.exchange is not None:
+                if self._n_sub >= 2:
+                    self.exchange.push(self.msgs[1 - c], s)
+                self.exchange.push(self.msgs[c], s)
             self._in_flight = False
         return self._views(c)
 
@@ -350,29 +375,34 @@ class PostBackbone:
                                                    m + 4 * self.bs, sp), "yc_nms_from_candidates")
         _lib.check(_lib.lib.yc_nms_workspace_reset(C.byref(self.nms_params), self.wss[c].data_ptr(), self.wss[c].numel(), sp),
                    "yc_nms_workspace_reset")
-        if self.exchange is not None:
-            # multi-GPU: this batch's detections go straight into every rank's receive buffer (one kernel, NVLink peer
-            # stores), then the messages of the PREVIOUS batch are awaited -- the one-step slack keeps the wait from
-            # ever spinning in the steady state while still bounding how far ranks can drift apart
-            self.exchange.push(self.msgs[c], stream)
-            self.exchange.wait(stream, lag=1)
 
     def attach_exchange(self, exchange):
         """Multi-GPU: `exchange` (parallel.PeerExchange built with this pipeline's hdr_ints / bs) receives every batch's
-        detections from the pipelined steps (submit / drain): the push and wait kernels run on the tail stream behind the
-        NMS kernels, inside the per-step CUDA graph.  After drain(), call exchange.wait() once more for the last batch."""
+        detections.  Pipelined steps (submit / drain): the push and wait kernels form a third branch of the per-step CUDA
+        graph, next to the head kernel and the NMS kernels (behind the NMS kernels they would lengthen the critical
+        branch: each small kernel costs 5-10 us next to the persistent head kernel): the graph of batch i pushes the
+        results of batch i - 2 and awaits earlier messages; drain() pushes the last two batches.  The i-th batch of a
+        stream carries the i-th sequence number; call exchange.wait_all() after drain().  Eager run_device() calls push and
+        await on the tail stream behind the NMS kernels."""
         if exchange is not None and (exchange.hdr_ints != self.hdr_ints or exchange.bs != self.bs):
             raise _lib.YcError("exchange was built for another message layout")
+        if self._in_flight:
+            raise _lib.YcError("attach_exchange() while a submit() batch is in flight: call drain() first")
         self.exchange = exchange
         self._pgraphs.clear()
+        if exchange is not None and self.xchg_stream is None:
+            self.xchg_stream = torch.cuda.Stream(device=self.device)
 
-    def _pipelined_step(self, features, c, with_tail=True):
+    def _pipelined_step(self, features, c, with_tail=True, with_push=False):
         """(captured) head of the current batch into workspace c  ||  NMS kernels of the previous batch (workspace
-        1-c); with_tail=False (first step of a stream of batches): the head kernel only."""
+        1-c)  ||  (with_push) exchange of the batch before that (output buffer c); with_tail=False (first step of a
+        stream of batches): the head kernel only."""
         main = torch.cuda.current_stream()
         side = self.tail_stream
         if with_tail:
             side.wait_stream(main)                               # fork
+        if with_push:
+            self.xchg_stream.wait_stream(main)
         for i, x in enumerate(features):
             self.desc.level[i].x = x.data_ptr()
         _lib.check(_lib.lib.yc_detect_fused_head_noreset(C.byref(self.desc), C.byref(self.nms_params),
@@ -380,6 +410,11 @@ class PostBackbone:
                                                          C.c_void_p(main.cuda_stream)), "yc_detect_fused_head")
         if with_tail:
             self._tail(1 - c, side)
+        if with_push:
+            self.exchange.push(self.msgs[c], self.xchg_stream)
+            self.exchange.wait(self.xchg_stream, lag=1)
+            main.wait_stream(self.xchg_stream)
+        if with_tail:
             main.wait_stream(side)                               # join
 
     # ---- host path (the e2e call) -----------------------------------------------------------------
