@@ -328,20 +328,25 @@ class PostBackbone:
             # multi-GPU: from the third batch on the graph has a third branch that pushes the results of the batch before
             # the previous one (complete since the previous graph) to all ranks and awaits earlier messages
             with_push = self.exchange is not None and self._n_sub >= 3
-            key = tuple(x.data_ptr() for x in features) + (c, with_push)
-            g = self._pgraphs.get(key)
+            ptrs = tuple(x.data_ptr() for x in features)
+            g = self._pgraphs.get(ptrs + (c, with_push))
             if g is None:
+                # a new set of input tensors: capture every variant of the step for it at once (both output buffers, with
+                # and without the exchange branch), so that no later step of the stream has to stop for a capture
                 for i, x in enumerate(features):
                     self._check(i, x)
                 torch.cuda.current_stream().wait_event(self.ev_tail[0])
                 torch.cuda.current_stream().wait_event(self.ev_tail[1])
                 torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
-                    self._pipelined_step(features, c, with_push=with_push)
-                if len(self._pgraphs) > 16:
+                if len(self._pgraphs) > 32:
                     self._pgraphs.clear()
-                self._pgraphs[key] = g
+                for cc in (0, 1):
+                    for wp in ((False, True) if self.exchange is not None else (False,)):
+                        gg = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gg, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
+                            self._pipelined_step(features, cc, with_push=wp)
+                        self._pgraphs[ptrs + (cc, wp)] = gg
+                g = self._pgraphs[ptrs + (c, with_push)]
             g.replay()
             self._in_flight = True
         return None if prev is None else self._views(prev)
