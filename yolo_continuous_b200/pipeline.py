@@ -360,10 +360,14 @@ class PostBackbone:
         with torch.cuda.device(self.device):
             c = self.cur
             s = torch.cuda.current_stream()
+            if self.exchange is not None and self._n_sub >= 2:
+                # the batch before the last is complete already: its push runs next to the last batch's NMS kernels
+                self.xchg_stream.wait_stream(s)
+                self.exchange.push(self.msgs[1 - c], self.xchg_stream)
             self._tail(c, s)
             if self.exchange is not None:
                 if self._n_sub >= 2:
-                    self.exchange.push(self.msgs[1 - c], s)
+                    s.wait_stream(self.xchg_stream)
                 self.exchange.push(self.msgs[c], s)
             self._in_flight = False
         return self._views(c)
