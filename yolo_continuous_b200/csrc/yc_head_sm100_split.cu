@@ -18,7 +18,8 @@
 // Tile = 128 pixels x ONE anchor (npad = round_up(no, 16) <= 128 columns): main + correction = 256 TMEM columns, double
 // buffered; the three anchors of a pixel block are consecutive tiles, which run on neighbouring SMs at the same time, so
 // the block's feature maps come from HBM once and from L2 twice.
-// Warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-7 converters, then 4 epilogue warps (12 for IBin).
+// Warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, then one or two groups of four converter warps, then 4
+// epilogue warps (12 for IBin).
 #include "yc_head_tc.cuh"
 
 namespace yc {
@@ -28,8 +29,7 @@ constexpr int TS_A_BYTES = TC_BM * TS_BK * 4;   // 16 KB: float32 landing buffer
 constexpr int TS_B_HALF = 128 * TS_BK * 2;      // 8 KB: w_hi (or w_lo) rows of up to 128 columns, two {64 n, 32 k} boxes
 constexpr int TS_STAGE_BYTES = TS_A_BYTES + 2 * TS_B_HALF;   // 32 KB
 constexpr int TS_MAX_STAGES = 6;
-constexpr int TS_NON_EPI_WARPS = 8;
-constexpr int TS_CONV_BAR_ID = 9;               // named barrier of the four converter warps (1..8 belong to the IBin epilogue)
+constexpr int TS_CONV_BAR_ID = 9;               // named barriers 9, 10 of the converter groups (1..8 belong to the IBin epilogue)
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b)
 {
@@ -37,9 +37,13 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b)
     return *(const uint32_t *)&h;
 }
 
+// NCG converter groups of four warps each take alternate k-blocks: one group converts a stage in ~600 cycles (8 LDS.128,
+// ~160 ALU instructions and 8 STS.128 per thread behind a 128-thread barrier), more than the stage's six MMAs take
+template <int NCG>
 __global__ void __maxnreg__(96)
 head_tcs_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
+    constexpr int TS_NON_EPI_WARPS = 4 + 4 * NCG;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *stage_base = smem;
@@ -178,15 +182,19 @@ head_tcs_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
         // thread -> k-row (lane) of the 32-pixel box `pq` (warp): 8 x LDS.128 along the swizzled 128-byte row, then (after
         // all four warps have read everything: the outputs overwrite other threads' inputs) 4 + 4 x STS.128 into rows of
         // the two fp16 operands, same swizzle (16-byte chunk index ^ (row & 7)) as TMA would have written
-        const int pq = warp - 4, k = lane;
+        const int cg = (warp - 4) >> 2, pq = (warp - 4) & 3, k = lane;   // converter group, pixel quarter, k-row
         const uint32_t sw = (uint32_t)(k & 7);
         const float down = 1.0f / (float)(1 << YC_SPLIT_XSHIFT);
-        int stage = 0;
+        int stage = 0, gk = 0;   // gk: k-blocks seen so far (group cg converts those with gk % NCG == cg)
         uint32_t phase = 0;
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
             const TileCoord tc = coord(t);
             const int nkb = (P.lv[tc.lv].K + TS_BK - 1) / TS_BK;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nkb; ++kb, ++gk) {
+                if (NCG > 1 && gk % NCG != cg) {
+                    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+                    continue;
+                }
                 uint8_t *sa = stage_base + stage * TS_STAGE_BYTES;
                 mbar_wait(&full_bar[stage], phase);
                 if (P.debug & 64) {
@@ -199,7 +207,7 @@ head_tcs_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                 const uint8_t *src = sa + pq * 4096 + k * 128;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = *(const float4 *)(src + (((uint32_t)c ^ sw) << 4));
-                named_bar_sync(TS_CONV_BAR_ID, 128);
+                named_bar_sync(TS_CONV_BAR_ID + cg, 128);
                 uint8_t *dhi = sa + (pq >> 1) * 4096 + k * 128, *dlo = dhi + 8192;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {   // 8 pixels per 16-byte chunk
@@ -274,6 +282,7 @@ int launch_head_split(const yc_head_desc *d, int rows_total, const int *row_off,
     const uint32_t slab_bytes = ibin ? (uint32_t)round_up(32 * no_out * 4 + (any_raw ? 32 * d->no * 4 : 0), 16)
                                      : (uint32_t)round_up(32 * d->no * 4, 16);
     const int epi_warps = ibin ? 12 : 4;
+    const int ncg = ibin ? 1 : 2;      // converter groups (IBin's 12 epilogue warps leave threads / registers for one)
     const size_t fixed = 1024 + (size_t)4 * slab_bytes + 256;
     int stages = TS_MAX_STAGES;
     while (stages > 2 && fixed + (size_t)stages * TS_STAGE_BYTES > 227 * 1024) --stages;
@@ -356,9 +365,10 @@ int launch_head_split(const yc_head_desc *d, int rows_total, const int *row_off,
     }
     P.total_tiles = tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    const int threads = 32 * (TS_NON_EPI_WARPS + epi_warps);
-    YC_CUDA(cudaFuncSetAttribute(head_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    head_tcs_kernel<<<grid, threads, smem_bytes, stream>>>(maps, P);
+    const int threads = 32 * (4 + 4 * ncg + epi_warps);
+    void (*kern)(const TcMaps, const TcParams) = ncg == 2 ? head_tcs_kernel<2> : head_tcs_kernel<1>;
+    YC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kern<<<grid, threads, smem_bytes, stream>>>(maps, P);
     YC_CUDA(cudaGetLastError());
     return YC_OK;
 }
