@@ -212,6 +212,13 @@ def load_peaks():
         return {}, "fallback"
 
 
+def traffic_of(key):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(key)
+    except (OSError, ValueError):
+        return None
+
+
 def other_configs(dev, peaks):
     """The other configurations of BASELINE.json on one GPU, device-resident, each with images/s and the fraction of the
     roofline that bounds it (HBM unless stated).  They are parity-test cases first (tests/), measured here so that the
@@ -309,7 +316,8 @@ def other_configs(dev, peaks):
         "forward_ms": ms_f, "forward_images_per_s": 64 / ms_f * 1e3, "step_ms": ms_s, "images_per_s": 64 / ms_s * 1e3,
         "detections_per_step": int(pipe.meta[64:][-1]),
         "roofline": {"bound": "hbm", "achieved": BYTES_PER_IMG["fp32"] * 64 / (ms_f / 1e3) / 1e9, "peak": hbm / 1e9,
-                     "unit": "GB/s", "frac": BYTES_PER_IMG["fp32"] * 64 / (ms_f / 1e3) / hbm,
+                     "unit": "GB/s", "frac": BYTES_PER_IMG["fp32"] * 64 / (ms_f / 1e3) / hbm, "traffic": traffic_of("head_fp32_bs64"),
+                     "kernel": "head_tcs_kernel (float32 maps split into fp16 hi/lo in the kernel, 3 tcgen05 MMAs per k-step)",
                      "tensor_tflops": FLOPS_PER_IMG * 64 / (ms_f / 1e3) / 1e12,
                      "note": "S1 fp32: 20.04 MB/img (maps in + z out), ceiling 327 k img/s"}}
     return out
