@@ -294,9 +294,20 @@ def other_configs(dev, peaks):
             z = head(list(xs))[0]
         byts = (elems5 * 2 + z.shape[1] * z.shape[2] * 4) * bs5
         flops = 2 * head.na * head.no * elems5 * bs5
-        out[name] = {"config": f"C5: {cls.__name__}.forward -> z at 1280x1280, batch 16, bf16 maps (z only; "
-                               f"{'aux convolution skipped, ' if cls is IAuxDetect else ''}module call incl. allocation)",
+        # the whole step (head -> NMS, z never written) through the pipelined fused path, C2 thresholds
+        head.return_raw = True
+        pipe = PostBackbone(head, bs5, shapes5, torch.bfloat16, (1280, 1280), (720, 1280), True, CONF, IOU, dev,
+                            use_graph=False, overlap=True)
+        ms_step, det = pipelined(pipe, xs[:3], 10, 3)
+        fused_step = pipe.fused
+        del pipe
+        out[name] = {"config": f"C5: {cls.__name__} at 1280x1280, batch 16, bf16 maps: forward -> z (z only; "
+                               f"{'aux convolution skipped, ' if cls is IAuxDetect else ''}module call incl. allocation) and "
+                               f"the fused step head -> NMS (conf {CONF} / iou {IOU}, pipelined graphs)",
                      "forward_ms": ms, "images_per_s": bs5 / ms * 1e3,
+                     "step_ms": ms_step, "step_images_per_s": bs5 / ms_step * 1e3, "step_detections": det, "step_fused": fused_step,
+                     "step_roofline": {"bound": "hbm", "frac": elems5 * 2 * bs5 / (ms_step / 1e3) / hbm,
+                                       "tensor_frac": 2 * head.na * head.no * elems5 * bs5 / (ms_step / 1e3) / tpeak},
                      "roofline": {"bound": "hbm", "achieved": byts / (ms / 1e3) / 1e9, "peak": hbm / 1e9, "unit": "GB/s",
                                   "frac": byts / (ms / 1e3) / hbm, "tensor_tflops": flops / (ms / 1e3) / 1e12}}
         del xs, z
