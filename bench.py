@@ -284,7 +284,13 @@ def other_configs(dev, peaks):
     bs5 = 16
     elems5 = sum(c * h * w for c, (h, w) in zip(CH, shapes5))
     for name, cls, ch in (("c5_iauxdetect_1280_bs16", IAuxDetect, CH * 2), ("c5_ibin_1280_bs16", IBin, CH)):
-        head = cls(NC, COCO_ANCHORS, ch).to(dev).eval()
+        head = cls(NC, COCO_ANCHORS, ch).eval()
+        with torch.no_grad():   # trained-like objectness / class biases (as make_params): ~10^2 candidates per image
+            for conv in head.m:
+                b = conv.bias.view(head.na, head.no)
+                b[:, head.no - NC - 1] -= 5.0
+                b[:, head.no - NC:] -= 3.0
+        head = head.to(dev)
         head.stride = torch.tensor(STRIDES)
         head.return_raw = False
         head.compute_aux_in_eval = False   # the reference's dead aux convolution in eval (nets/iaux_detect.py:37-38)
