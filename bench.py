@@ -286,10 +286,16 @@ def other_configs(dev, peaks):
     for name, cls, ch in (("c5_iauxdetect_1280_bs16", IAuxDetect, CH * 2), ("c5_ibin_1280_bs16", IBin, CH)):
         head = cls(NC, COCO_ANCHORS, ch).eval()
         with torch.no_grad():   # trained-like objectness / class biases (as make_params): ~10^2 candidates per image
-            for conv in head.m:
+            for im in head.im:   # ImplicitM ~ N(1, .02) as make_params (the reference's N(0, .02) scales every logit to ~0)
+                im.implicit.copy_(1.0 + 0.02 * torch.randn(im.implicit.shape, generator=torch.Generator().manual_seed(11)))
+            g5 = torch.Generator().manual_seed(12)
+            for conv in head.m:      # objectness / class logits ~ N(-5, 1.5) / N(-3, 1.5), as make_params
+                k = conv.weight.shape[1]
+                w = conv.weight.view(head.na, head.no, k)
+                w[:, head.no - NC - 1:, :] = torch.randn(head.na, NC + 1, k, generator=g5) * (1.5 / k ** 0.5)
                 b = conv.bias.view(head.na, head.no)
-                b[:, head.no - NC - 1] -= 5.0
-                b[:, head.no - NC:] -= 3.0
+                b[:, head.no - NC - 1] = -5.0
+                b[:, head.no - NC:] = -3.0
         head = head.to(dev)
         head.stride = torch.tensor(STRIDES)
         head.return_raw = False

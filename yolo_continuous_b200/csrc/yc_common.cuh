@@ -79,9 +79,14 @@ __host__ __device__ inline BlobView blob_view(const void *blob, int N, int K)
 // ---- numerics shared by every decode epilogue ---------------------------------------------
 // sigmoid in binary32: 1/(1+exp(-t)).  ex2.approx + rcp keep the relative error near 3e-7,
 // inside the 1e-5 parity bound with margin.
+// (.ftz forms: two MUFU operations and three FP32 instructions per value; the plain forms add a range check and two
+// predicated multiplies per value for operands that cannot change a sigmoid -- 1 + a denormal is 1.)
 __device__ __forceinline__ float sigmoidf_fast(float t)
 {
-    return __fdividef(1.0f, 1.0f + __expf(-t));
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
 }
 
 // xy = (s*2 - 0.5 + g) * stride, evaluated in the reference's operation order

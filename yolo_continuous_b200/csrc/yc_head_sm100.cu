@@ -43,7 +43,8 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     float *slabs = (float *)(smem + n_stages * TC_STAGE_BYTES);
     const int n_epi_warps = P.epi_warps;
     const int n_slabs = P.ibin ? 4 : n_epi_warps;   // IBin: one slab per TMEM lane quadrant, shared by its three warps
-    uint64_t *bars = (uint64_t *)((uint8_t *)slabs + (size_t)n_slabs * P.slab_bytes);
+    float2 *sbtab = (float2 *)((uint8_t *)slabs + (size_t)n_slabs * P.slab_bytes);   // half-row epilogue: (scale, bias) of every level
+    uint64_t *bars = (uint64_t *)(sbtab + P.tab_entries);
     uint64_t *full_bar = bars;                        // [TC_MAX_STAGES]
     uint64_t *empty_bar = bars + TC_MAX_STAGES;       // [TC_MAX_STAGES]
     uint64_t *tfull_bar = bars + 2 * TC_MAX_STAGES;   // [2]
@@ -70,6 +71,10 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr_smem, TC_TMEM_COLS);
+    if (P.tab_entries) {   // level s, column c of the head at [s * na_real * no + c]
+        const int n_head = P.na_real * P.no;
+        for (int i = threadIdx.x; i < P.tab_entries; i += blockDim.x) sbtab[i] = __ldg(P.lv[i / n_head].sb + i % n_head);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -195,6 +200,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         float *slab = (float *)((uint8_t *)slabs + (size_t)e * P.slab_bytes);
         int it = 0, cur_key = -1;
         BoxSb sbv;
+        long long pf[4] = {0, 0, 0, 0}, pf_wait = 0, pf_t0 = DBG ? clock64() : 0;
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
             const TileCoord tc = tile_coord(P, t);
             const TcLevel &L = P.lv[tc.lv];
@@ -211,8 +217,10 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 sbv = load_box_sb(sb, lane, P.nc);
                 cur_key = tc.lv * YC_MAX_ANCHORS + tc.g;
             }
+            const long long w0 = prof ? clock64() : 0;
             mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
+            if (prof) pf_wait += clock64() - w0;
             if (skip_epi) {
                 tc_fence_before();
                 __syncwarp();
@@ -224,9 +232,17 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 else fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane, sbv);
                 continue;
             }
+            if (P.half_off) {
+                store_rows_half_any<false>(P, L, tc.b, prow0, nv, ar, taddr, smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no),
+                                           smem_addr(slab), &tempty_bar[buf], lane, prof ? pf : nullptr);
+                continue;
+            }
             store_epilogue<false>(P, L, tc.b, tc.p0, tc.g, e, q, lane, tmem_base + (uint32_t)(buf * TC_MAX_N), (uint8_t *)slabs,
-                                  &tempty_bar[buf]);
+                                  &tempty_bar[buf], prof ? pf : nullptr);
         }
+        if (prof && lane == 0)
+            printf("[yc prof] epilogue warp %d: %d tiles, total %lld cyc: waiting tfull %lld, slab read-out %lld, tmem+decode %lld, "
+                   "store issue %lld, named barriers %lld\n", e, it, clock64() - pf_t0, pf_wait, pf[0], pf[1], pf[2], pf[3]);
         if (lane == 0) bulk_wait_all0(); // global writes complete before the CTA exits
     }
 
@@ -300,9 +316,14 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     // IBin: one slab per quadrant holding the z rows and (if asked for) the raw rows of 32 pixels
     bool any_raw = false;
     for (int i = 0; i < d->nl; ++i) any_raw = any_raw || d->level[i].raw != nullptr;
+    // z / raw rows by halves (store_rows_half): 16-row slabs and the (scale, bias) table in shared memory
+    int half_off = (!fused && !ibin) ? half_off_for(d->no, na_tile) : 0;
+    { const char *e = getenv("YC_TC_HALF"); if (e && atoi(e) == 0) half_off = 0; }   // experiments: the whole-row epilogue
+    const int tab_entries = half_off ? d->nl * N : 0;
+    if (tab_entries * 8 > 16 * 1024) half_off = 0;
     const uint32_t slab_bytes = fused ? (uint32_t)round_up(TC_QUEUE_ROWS * (d->no - 5) * 4, 16)
                                 : ibin ? (uint32_t)round_up(32 * no_out * 4 + (any_raw ? 32 * d->no * 4 : 0), 16)
-                                       : (uint32_t)round_up(32 * d->no * 4, 16);
+                                       : (uint32_t)round_up((half_off ? 16 : 32) * d->no * 4, 16);
     const int epi_warps = ibin ? (fused ? 4 : 12) : 4 * na_tile;   // fused IBin: one warp per quadrant (most rows stop at the objectness)
     // K=64 per stage: 4 stages in the fused mode (no z slabs in shared memory), 2 next to the slabs.
     // (K=128 x 2 stages measured 6 us slower on the C2 batch; YC_TC_BK overrides for experiments.)
@@ -310,13 +331,16 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     { const char *e = getenv("YC_TC_BK"); if (e && (atoi(e) == 64 || atoi(e) == 128)) bk = atoi(e); }
     // CTA pairs (cta_group::2) for the fused step: see yc_head_sm100_2cta.cu (measured 2-4 % faster than the 1-CTA
     // kernel for batches of 32 images and more: 8 feature-map stages instead of 4).  YC_TC_2CTA=0 keeps the 1-CTA kernel.
-    bool pair = fused != nullptr && n_groups == 1 && npad % 16 == 0;
+    // (r03) the z-writing forward takes the pair kernel too when its rows go by halves: per tile the 1-CTA kernel streams
+    // all of W from L2 (777 MB per C2 batch next to 367 MB of maps) through a ring that the slabs leave 2-3 stages deep
+    bool pair = (fused != nullptr || half_off > 0) && n_groups == 1 && npad % 16 == 0;
     { const char *e = getenv("YC_TC_2CTA"); if (e && atoi(e) == 0) pair = false; }
     if (pair) bk = T2_BK; // feature-map box height of the CTA-pair kernel
     const int tile_px = pair ? 2 * TC_BM : TC_BM;
     const uint32_t b_slot_bytes = (uint32_t)round_up(npad * 64 * 2, 1024);   // npad is a multiple of 16: 2 KB steps
     const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * b_slot_bytes;
-    const size_t fixed = 1024 + (size_t)(ibin ? 4 : 4 * na_tile) * slab_bytes + 256;   // (fused IBin: 4 warps x one area each)
+    const size_t fixed = 1024 + (size_t)(ibin ? 4 : 4 * na_tile) * slab_bytes + 256 +   // (fused IBin: 4 warps x one area each)
+                         (half_off ? (size_t)tab_entries * 8 : 0);
     int stages = TC_MAX_STAGES;
     while (stages > 2 && fixed + (size_t)stages * stage_bytes > 227 * 1024) --stages;
     const size_t smem_bytes = fixed + (size_t)stages * stage_bytes;
@@ -364,6 +388,8 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     P.b_slot_bytes = b_slot_bytes;
     P.slab_bytes = slab_bytes;
     P.stages = stages;
+    P.half_off = half_off;
+    P.tab_entries = half_off ? n * N : 0;   // levels in schedule order (those that meet the TMA rules)
     { const char *e = getenv("YC_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
     if (fused) {
         P.fused = 1; P.nc = fused->nc; P.conf = fused->conf; P.div_w = fused->div_w; P.div_h = fused->div_h;

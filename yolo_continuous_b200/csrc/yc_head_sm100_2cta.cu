@@ -58,7 +58,8 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
     R.b_slots = smem + na_st * T2_A_BYTES;
     R.queues = (float *)(R.b_slots + T2_B_SLOTS * T2_B_BYTES);
     const int n_epi_warps = 4 * P.na;
-    uint64_t *bars = (uint64_t *)((uint8_t *)R.queues + (size_t)n_epi_warps * P.slab_bytes);
+    float2 *sbtab = (float2 *)((uint8_t *)R.queues + (size_t)n_epi_warps * P.slab_bytes);   // z-writing mode: (scale, bias) table
+    uint64_t *bars = (uint64_t *)(sbtab + P.tab_entries);
     R.a_full = bars;
     R.a_empty = R.a_full + T2_MAX_A_STAGES;
     R.b_full = R.a_empty + T2_MAX_A_STAGES;
@@ -94,6 +95,10 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_pair(R.tmem_ptr, TC_TMEM_COLS);
+    if (P.tab_entries) {   // level s, column c of the head at [s * na_real * no + c]
+        const int n_head = P.na_real * P.no;
+        for (int i = threadIdx.x; i < P.tab_entries; i += blockDim.x) sbtab[i] = __ldg(P.lv[i / n_head].sb + i % n_head);
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync(); // both CTAs' barriers are initialised before any remote arrive / TMA completion
@@ -260,7 +265,7 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
             const int nv = img < P.bs ? min(32, L.HW - prow0) : 0;
             const int ar = a;
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_MAX_N + a * P.no);
-            if (tc.lv != cur_lv) { // fused mode: one anchor group per tile, so `ar` is fixed for this warp
+            if (P.fused && tc.lv != cur_lv) { // one anchor group per tile, so `ar` is fixed for this warp
                 sbv = load_box_sb(L.sb + ar * P.no, lane, P.nc);
                 cur_lv = tc.lv;
             }
@@ -274,7 +279,11 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                 if (lane == 0) mbar_arrive_leader(&R.tempty[buf]);
                 continue;
             }
-            fused_epilogue<true>(P, L, img, prow0, nv, ar, taddr, slab, &R.tempty[buf], lane, sbv);
+            if (P.fused)
+                fused_epilogue<true>(P, L, img, prow0, nv, ar, taddr, slab, &R.tempty[buf], lane, sbv);
+            else   // z / raw maps (the drop-in forward): rows by halves through the warp's 16-row slab
+                store_rows_half_any<true>(P, L, img, prow0, nv, ar, taddr, smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no),
+                                          smem_addr(slab), &R.tempty[buf], lane);
             if (eprof) {
                 const long long e2 = clock64();
                 e_wait += e1 - e0;
@@ -286,6 +295,7 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
         if (eprof && lane == 0)
             printf("[yc prof2] epilogue warp %d: %d tiles, waiting tfull %lld, working %lld (max %lld per tile, %d tiles > 600)\n",
                    e, it, e_wait, e_work, e_max, e_slow);
+        if (!P.fused && lane == 0) bulk_wait_all0();   // global writes complete before the CTA exits
     }
 
     tc_fence_before();
@@ -298,11 +308,12 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
 // host side: same descriptors as the 1-CTA kernel; only the weight box (half the rows) and the grid differ
 int launch_head_tc2(const TcMaps &maps, TcParams &P, int num_sms, cudaStream_t stream)
 {
-    const size_t fixed = 1024 + (size_t)4 * P.na * P.slab_bytes + 512 + (size_t)T2_B_SLOTS * T2_B_BYTES;
-    // at most 214 KB: the rest of the SM's 228 KB stays free for the NMS kernels of the previous batch, which run next
-    // to this kernel on a second stream (largest of them: 17.5 KB + 1 KB reserved per CTA)
+    const size_t fixed = 1024 + (size_t)4 * P.na * P.slab_bytes + 512 + (size_t)T2_B_SLOTS * T2_B_BYTES + (size_t)P.tab_entries * 8;
+    // fused step: at most 214 KB -- the rest of the SM's 228 KB stays free for the NMS kernels of the previous batch, which
+    // run next to this kernel on a second stream (largest of them: 17.5 KB + 1 KB reserved per CTA)
+    const size_t cap = (P.fused ? 214 : 227) * 1024;
     int stages = T2_MAX_A_STAGES;
-    while (stages > 2 && fixed + (size_t)stages * T2_A_BYTES > 214 * 1024) --stages;
+    while (stages > 2 && fixed + (size_t)stages * T2_A_BYTES > cap) --stages;
     const size_t smem_bytes = fixed + (size_t)stages * T2_A_BYTES;
     YC_REQUIRE(smem_bytes <= 227 * 1024, YC_ERR_UNSUPPORTED, "2-CTA head: needs %zu bytes of shared memory", smem_bytes);
     P.stages = stages;

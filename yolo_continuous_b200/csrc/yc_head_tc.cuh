@@ -71,8 +71,11 @@ struct TcParams {
     uint32_t b_box_bytes;      // npad * 64 * 2: bytes one weight box brings
     uint32_t b_slot_bytes;     // room one weight box takes in a stage of the 1-CTA kernel (b_box_bytes rounded up to 1 KB)
     uint32_t slab_bytes;       // per epilogue warp: 32*no*4 (z slab) or TC_QUEUE_ROWS*nc*4 (fused survivor queue)
-    int debug;                 // YC_TC_DEBUG bits (timing experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA
+    int debug;                 // YC_TC_DEBUG bits (timing experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA,
+                               // 128 z epilogue without the TMEM reads / decode (stores only), 256 without the stores
     int stages;                // depth of the smem ring
+    int half_off;              // > 0: z / raw rows are produced by halves (store_rows_half<half_off>), see there
+    int tab_entries;           // (scale, bias) pairs staged in shared memory: n_lv * na_real * no (half-row epilogue)
     int a_kmajor;              // feature maps are channels-last: A is a K-major operand
     // fused mode (yc_detect_fused): the epilogue thresholds and emits NMS candidates, z is never written
     int fused;
@@ -163,7 +166,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, int c0, const float2 *
     ld_acc<W, SPLIT>(taddr + (uint32_t)c0, v);
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        const float2 s_b = __ldg(sb + c0 + j); // same address for the whole warp: one broadcast load
+        const float2 s_b = YC_SB(sb + c0 + j); // same address for the whole warp: one broadcast load
         const float t = fmaf(__uint_as_float(v[j]), s_b.x, s_b.y);
         float r;
         if (RAW) {
@@ -207,7 +210,7 @@ __device__ __forceinline__ void ibin_chunk(uint32_t taddr, int c0, const float2 
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         const int o = c0 + j;
-        const float2 s_b = __ldg(sb + o);
+        const float2 s_b = YC_SB(sb + o);
         const float sg = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
         if (o < 2) {
             srow[o] = o == 0 ? decode_xy(sg, gx, stride) : decode_xy(sg, gy, stride_y);
@@ -235,7 +238,7 @@ __device__ __forceinline__ void sig_chunk(uint32_t taddr, int c0, const float2 *
     ld_acc<W, SPLIT>(taddr + (uint32_t)c0, v);
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        const float2 s_b = __ldg(sb + c0 + j);
+        const float2 s_b = YC_SB(sb + c0 + j);
         srow[c0 + j - shift] = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
     }
 }
@@ -438,8 +441,11 @@ __device__ __forceinline__ void slab_store(float *__restrict__ gdst, const float
 // first of them stores (named barriers 1..4 and 5..8, 96 threads each).
 template <bool SPLIT>
 __device__ __forceinline__ void store_epilogue(const TcParams &P, const TcLevel &L, int b, int p0, int g, int e, int q, int lane,
-                                               uint32_t tmem_tile, uint8_t *slabs, uint64_t *tempty)
+                                               uint32_t tmem_tile, uint8_t *slabs, uint64_t *tempty, long long *pf = nullptr)
 {
+    // pf (timing experiments, YC_TC_DEBUG bit 8): cycles spent [0] waiting for the slab's previous store to be read out,
+    // [1] in the TMEM reads + decode, [2] issuing the store, [3] IBin: in the named barriers
+    long long c0_ = pf ? clock64() : 0;
     const int no = P.no, no_out = P.no_out;
     const int a = P.ibin ? 0 : e >> 2;          // anchor of the tile handled by this warp (IBin: one anchor per tile)
     const int prow0 = p0 + 32 * q;              // first pixel of this warp's 32 rows
@@ -459,7 +465,9 @@ __device__ __forceinline__ void store_epilogue(const TcParams &P, const TcLevel 
             if (lane == 0) bulk_wait_read0();   // the previous stores from this quadrant's slab have been read out
             __syncwarp();
         }
+        if (pf) { const long long c = clock64(); pf[0] += c - c0_; c0_ = c; }
         named_bar_sync(1 + q, 96);
+        if (pf) { const long long c = clock64(); pf[3] += c - c0_; c0_ = c; }
         // part 0: [x y | w block]   part 1: [h block] + objectness and a third of the classes   part 2: the rest
         const int cb = part == 0 ? 0 : (part == 1 ? 2 + len : sc), ce = part == 0 ? 2 + len : (part == 1 ? sc : no);
         if (L.raw) epi_range_raw<SPLIT>(taddr, cb, ce, sb, rs + lane * no);
@@ -476,13 +484,16 @@ __device__ __forceinline__ void store_epilogue(const TcParams &P, const TcLevel 
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty);
+        if (pf) { const long long c = clock64(); pf[1] += c - c0_; c0_ = c; }
         named_bar_sync(5 + q, 96);              // all three parts of the rows are in the slab
+        if (pf) { const long long c = clock64(); pf[3] += c - c0_; c0_ = c; }
         if (part == 0 && nv > 0) {
             if (L.raw) slab_store(L.raw + (((size_t)b * P.na_real + ar) * L.HW + prow0) * no, rs, nv, no, lane);
             if (P.write_z)
                 slab_store(P.z + ((size_t)b * P.rows_total + L.row_off + (size_t)ar * L.HW + prow0) * no_out, zs, nv,
                            no_out, lane);
         }
+        if (pf) pf[2] += clock64() - c0_;
         return;
     }
     float *slab = (float *)(slabs + (size_t)e * P.slab_bytes);
@@ -496,17 +507,178 @@ __device__ __forceinline__ void store_epilogue(const TcParams &P, const TcLevel 
     if (P.write_z) {
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
-        epi_row<false, SPLIT>(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, L.stride_y, aw, ah);
+        if (pf) { const long long c = clock64(); pf[0] += c - c0_; c0_ = c; }
+        if (!(P.debug & 128)) epi_row<false, SPLIT>(taddr, no, sb, slab + lane * no_out, gx, gy, L.stride, L.stride_y, aw, ah);
     }
     // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA warp
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(tempty);
-    if (P.write_z && nv > 0)
+    if (pf) { const long long c = clock64(); pf[1] += c - c0_; c0_ = c; }
+    if (P.write_z && nv > 0 && !(P.debug & 256))
         slab_store(P.z + ((size_t)b * P.rows_total + L.row_off + (size_t)ar * L.HW + prow0) * no_out, slab, nv,
                    no_out, lane);
+    if (pf) pf[2] += clock64() - c0_;
 }
 
+
+
+// ---- z / raw epilogue by half rows ---------------------------------------------------------------------------------
+// The whole-row form above gives a lane one row of the accumulator (tcgen05.ld .32x32b) and a warp a 32-row slab
+// (32 * no * 4 bytes: 130 KB for the twelve epilogue warps of a COCO tile, which leaves the 1-CTA kernel two pipeline
+// stages), reads TMEM in 16-column chunks with a wait after each, fetches (scale, bias) from global memory per column and
+// writes the slab with generic stores.  Measured on the C2 batch (YC_TC_DEBUG bit 8): 81 cycles per column and warp, 60 %
+// of what the two MUFU operations of a sigmoid allow, and the MMA warp waits for the 2-stage ring 68 % of the time.
+// This form reads the accumulator with the .16x32bx2 shape: a pass covers 16 rows, lanes 0-15 own the columns [0, OFF) of
+// their row and lanes 16-31 the columns [OFF, 2 OFF) (OFF ~ no / 2).  All of a thread's columns of a pass are fetched by
+// a few wide loads behind ONE wait (at most 64 registers), so that the sigmoids of a pass are independent instructions
+// and the TMEM buffer goes back to the MMA warp as soon as the second pass is in registers; the slab is 16 rows (half
+// the shared memory: three stages instead of two); (scale, bias) come from a table in shared memory; the slab is
+// written with st.shared.
+constexpr int HG = 8;   // columns per group of independent sigmoids in store_rows_half
+template <int OFF>
+__device__ __forceinline__ void ld_half_row(uint32_t ta, uint32_t *v)
+{
+    if constexpr ((OFF & 64) != 0) TmemLdHalf<64, OFF>::ld(ta, v);
+    if constexpr ((OFF & 32) != 0) TmemLdHalf<32, OFF>::ld(ta + (OFF & 64), v + (OFF & 64));
+    if constexpr ((OFF & 16) != 0) TmemLdHalf<16, OFF>::ld(ta + (OFF & 96), v + (OFF & 96));
+    if constexpr ((OFF & 8) != 0) TmemLdHalf<8, OFF>::ld(ta + (OFF & 112), v + (OFF & 112));
+    if constexpr ((OFF & 4) != 0) TmemLdHalf<4, OFF>::ld(ta + (OFF & 120), v + (OFF & 120));
+    if constexpr ((OFF & 2) != 0) TmemLdHalf<2, OFF>::ld(ta + (OFF & 124), v + (OFF & 124));
+    if constexpr ((OFF & 1) != 0) TmemLdHalf<1, OFF>::ld(ta + (OFF & 126), v + (OFF & 126));
+}
+
+// bulk store of `rows` finished rows (no floats each) of the 16-row slab; unaligned spans fall back to plain stores
+__device__ __forceinline__ void half_slab_store(float *__restrict__ gdst, uint32_t slab_s, int rows, int no, int lane)
+{
+    const uint32_t bytes = (uint32_t)rows * no * 4u;
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (rows <= 0) return;
+    if ((((uintptr_t)gdst | bytes) & 15u) == 0) {
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(slab_s), "r"(bytes) : "memory");
+            bulk_commit();
+        }
+    } else {
+        for (int i = lane; i < rows * no; i += 32) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(slab_s + 4u * i));
+            gdst[i] = v;
+        }
+    }
+}
+
+// One warp, one tile: the 32 pixels [prow0, prow0 + 32) of image b (nv of them exist) for anchor `ar` of the head.
+//   taddr   TMEM address of (first lane of the warp's quadrant, first accumulator column of the anchor)
+//   tab_s   shared address of the anchor's (scale, bias) pairs;  slab_s  shared address of the warp's 16-row slab
+//   PAIR    the TMEM-empty barrier lives in the pair's leader CTA
+template <int OFF, bool PAIR>
+__device__ __forceinline__ void store_rows_half(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar, uint32_t taddr,
+                                                uint32_t tab_s, uint32_t slab_s, uint64_t *tempty, int lane, long long *pf = nullptr)
+{
+    const int no = P.no;
+    const int half = lane >> 4, r = lane & 15;
+    const int cbase = half * OFF;                 // first column owned by this thread
+    const float aw = L.anchor_wh[2 * ar], ah = L.anchor_wh[2 * ar + 1];
+    const uint32_t srow = slab_s + (uint32_t)(r * no + cbase) * 4u, trow = tab_s + (uint32_t)cbase * 8u;
+    const int ncols = half == 0 ? OFF : max(0, min(OFF, no - OFF));   // columns of this thread that exist (the rest: next anchor)
+    long long c0_ = pf ? clock64() : 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        uint32_t v[OFF];
+        ld_half_row<OFF>(taddr + ((uint32_t)(16 * pass) << 16), v);
+        tmem_ld_wait();
+        if (pass == 1) {   // all TMEM reads of this warp are done: hand the accumulator buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_leader(tempty);
+                else mbar_arrive(tempty);
+            }
+        }
+        if (pf) { const long long c = clock64(); pf[3] += c - c0_; c0_ = c; }
+        const int rows = min(16, nv - 16 * pass);
+        const int p = prow0 + 16 * pass + r;
+        const size_t grow = (size_t)prow0 + 16 * pass;
+        if (L.raw) {       // forward()'s list `x`: the pre-sigmoid maps
+            if (lane == 0) bulk_wait_read0();   // the slab's previous store has been read out
+            __syncwarp();
+            if (pf) { const long long c = clock64(); pf[0] += c - c0_; c0_ = c; }
+            // (values first, stores after: the st.shared are volatile asm statements, which the compiler keeps in program
+            // order -- interleaved with the arithmetic they serialise every column behind the latency of the previous one)
+            // (HG values, then HG stores: the st.shared are volatile asm statements, which the compiler keeps in program order
+            // -- interleaved one by one with the arithmetic they serialise every column behind the latency of the previous one)
+#pragma unroll
+            for (int j0 = 0; j0 < OFF; j0 += HG) {
+                float w[HG];
+#pragma unroll
+                for (int j = j0; j < j0 + HG && j < OFF; ++j) {
+                    const float2 s_b = lds_f32x2(trow + 8u * j);
+                    w[j - j0] = fmaf(__uint_as_float(v[j]), s_b.x, s_b.y);
+                }
+#pragma unroll
+                for (int j = j0; j < j0 + HG && j < OFF; ++j)
+                    if (j < ncols) sts_f32(srow + 4u * j, w[j - j0]);
+            }
+            if (pf) { const long long c = clock64(); pf[1] += c - c0_; c0_ = c; }
+            half_slab_store(L.raw + (((size_t)b * P.na_real + ar) * L.HW + grow) * no, slab_s, rows, no, lane);
+            if (pf) { const long long c = clock64(); pf[2] += c - c0_; c0_ = c; }
+        }
+        if (P.write_z) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            if (pf) { const long long c = clock64(); pf[0] += c - c0_; c0_ = c; }
+            const float gx = (float)(p % L.nx), gy = (float)(p / L.nx);
+#pragma unroll
+            for (int j0 = 0; j0 < OFF; j0 += HG) {
+                float w[HG];
+#pragma unroll
+                for (int j = j0; j < j0 + HG && j < OFF; ++j) {
+                    const float2 s_b = lds_f32x2(trow + 8u * j);
+                    float sg = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
+                    if (j < 4 && half == 0) {   // box columns (nets/idetect.py:41-42); OFF >= 4, so they belong to the lower half
+                        if (j == 0) sg = decode_xy(sg, gx, L.stride);
+                        else if (j == 1) sg = decode_xy(sg, gy, L.stride_y);
+                        else if (j == 2) sg = decode_wh(sg, aw);
+                        else sg = decode_wh(sg, ah);
+                    }
+                    w[j - j0] = sg;
+                }
+#pragma unroll
+                for (int j = j0; j < j0 + HG && j < OFF; ++j)
+                    if (j < ncols) sts_f32(srow + 4u * j, w[j - j0]);
+            }
+            if (pf) { const long long c = clock64(); pf[1] += c - c0_; c0_ = c; }
+            half_slab_store(P.z + ((size_t)b * P.rows_total + L.row_off + (size_t)ar * L.HW + grow) * no, slab_s, rows, no, lane);
+            if (pf) { const long long c = clock64(); pf[2] += c - c0_; c0_ = c; }
+        }
+    }
+}
+
+// the OFF values instantiated (tcgen05.ld takes the half-split offset as an immediate)
+__host__ __device__ inline int half_off_for(int no, int na_tile)
+{
+    const int need = (no + 1) / 2;
+    const int cand[6] = {4, 8, 16, 32, 43, 64};
+    for (int i = 0; i < 6; ++i)   // lanes 16-31 read the columns [OFF, 2 OFF) of the LAST anchor too: they must stay inside the buffer
+        if (cand[i] >= need && cand[i] <= no && (na_tile - 1) * no + 2 * cand[i] <= TC_MAX_N) return cand[i];
+    return 0;
+}
+
+template <bool PAIR>
+__device__ __forceinline__ void store_rows_half_any(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar, uint32_t taddr,
+                                                    uint32_t tab_s, uint32_t slab_s, uint64_t *tempty, int lane, long long *pf = nullptr)
+{
+    switch (P.half_off) {
+    case 4: store_rows_half<4, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
+    case 8: store_rows_half<8, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
+    case 16: store_rows_half<16, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
+    case 32: store_rows_half<32, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
+    case 43: store_rows_half<43, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
+    default: store_rows_half<64, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
+    }
+}
 
 
 // Fused epilogue of one warp for one tile (see yc_detect_fused): reads this warp's 32 rows of the accumulator

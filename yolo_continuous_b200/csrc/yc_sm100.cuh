@@ -74,6 +74,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// shared memory by 32-bit shared-window address (pointers derived from the dynamic shared array through integer
+// arithmetic lose their address space and compile to generic LD / ST)
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t saddr)
+{
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));   // not volatile: tables that are constant after setup
+    return v;
+}
+
 // ---- TMA -------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m)
 {
@@ -263,6 +273,73 @@ template <> struct TmemLd<32> {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                      : "r"(taddr)
+                     : "memory");
+    }
+};
+// TMEM -> registers, shape .16x32bx2: 16 lanes starting at the lane of `taddr` (0 or 16 within the warp's quadrant);
+// threads 0-15 receive the W columns starting at the column of `taddr`, threads 16-31 the W columns OFF further on, of
+// the same 16 lanes.  A thread thus owns HALF a row of 16 rows instead of a whole row of 32 (tools/ldtm_probe.cu).
+template <int W, int OFF> struct TmemLdHalf;
+template <int OFF> struct TmemLdHalf<1, OFF> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x1.b32 {%0}, [%1], %2;"
+                     : "=r"(r[0])
+                     : "r"(taddr), "n"(OFF)
+                     : "memory");
+    }
+};
+template <int OFF> struct TmemLdHalf<2, OFF> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x2.b32 {%0, %1}, [%2], %3;"
+                     : "=r"(r[0]), "=r"(r[1])
+                     : "r"(taddr), "n"(OFF)
+                     : "memory");
+    }
+};
+template <int OFF> struct TmemLdHalf<4, OFF> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x4.b32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                     : "r"(taddr), "n"(OFF)
+                     : "memory");
+    }
+};
+template <int OFF> struct TmemLdHalf<8, OFF> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr), "n"(OFF)
+                     : "memory");
+    }
+};
+template <int OFF> struct TmemLdHalf<16, OFF> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16], %17;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr), "n"(OFF)
+                     : "memory");
+    }
+};
+template <int OFF> struct TmemLdHalf<32, OFF> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32], %33;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr), "n"(OFF)
+                     : "memory");
+    }
+};
+template <int OFF> struct TmemLdHalf<64, OFF> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t *r)
+    {
+        asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64], %65;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                     : "r"(taddr), "n"(OFF)
                      : "memory");
     }
 };

@@ -122,9 +122,8 @@ class HeadBase(nn.Module):
                 lv.x, lv.blob = x.data_ptr(), blob.data_ptr()
                 lv.K, lv.H, lv.W = k, h, w
                 if want_z:
-                    lv.stride = float(self.stride[i])  # TypeError when stride was never set, as the reference
-                ag = self.anchor_grid[i].reshape(-1).tolist()
-                for j, v in enumerate(ag):
+                    lv.stride = self._stride_list()[i]  # TypeError when stride was never set, as the reference
+                for j, v in enumerate(self._anchor_list(i)):
                     lv.anchor_wh[j] = v
                 if want_raw:
                     r = torch.empty((bs, self.na, h, w, self.no), dtype=torch.float32, device=dev)
@@ -140,6 +139,28 @@ class HeadBase(nn.Module):
                 d.bins = bins.data_ptr()
             _lib.check(_lib.lib.yc_head_forward(C.byref(d), _lib.stream_ptr(dev)), "yc_head_forward")
         return z, raws
+
+    def _stride_list(self):
+        st = self.stride
+        if not isinstance(st, torch.Tensor):
+            return [float(st[i]) for i in range(self.nl)]   # None: TypeError, as `self.stride[i]` in the reference
+        key = (st.data_ptr(), st._version)
+        hit = self._packed.get("stride")
+        if hit is None or hit[0] != key:
+            hit = (key, [float(v) for v in st.reshape(-1).tolist()])
+            self._packed["stride"] = hit
+        return hit[1]
+
+    def _anchor_list(self, i):
+        # anchor_grid lives on the device: reading it back is a stream synchronisation, so the host copy is cached on the
+        # buffer's identity and version (a reloaded or rescaled anchor_grid is read again)
+        ag = self.anchor_grid
+        key = (ag.data_ptr(), ag._version)
+        hit = self._packed.get("anchors")
+        if hit is None or hit[0] != key:
+            hit = (key, ag.reshape(self.nl, -1).tolist())
+            self._packed["anchors"] = hit
+        return hit[1][i]
 
     def _update_grid_cache(self, i, ny, nx, device):
         # attribute kept for compatibility with code that inspects `head.grid` (nets/idetect.py:37-38);
