@@ -77,15 +77,21 @@ __host__ __device__ inline BlobView blob_view(const void *blob, int N, int K)
 }
 
 // ---- numerics shared by every decode epilogue ---------------------------------------------
-// sigmoid in binary32: 1/(1+exp(-t)).  ex2.approx + rcp keep the relative error near 3e-7,
-// inside the 1e-5 parity bound with margin.
-// (.ftz forms: two MUFU operations and three FP32 instructions per value; the plain forms add a range check and two
-// predicated multiplies per value for operands that cannot change a sigmoid -- 1 + a denormal is 1.)
+// sigmoid in binary32: 1 / (1 + exp(-t)), relative error ~2e-7, inside the 1e-5 parity bound with
+// margin.  ONE special-function (MUFU) operation per value: the z-writing epilogues are bound by that pipe -- ncu on the
+// IBin forward: XU pipe 67 % busy at 17 cycles per warp instruction, with ex2 + rcp per sigmoid -- so the reciprocal runs
+// on the FMA pipe instead: exponent-trick seed (12 % off) and three Newton steps r <- r (2 - y r) (1.4e-2, 2e-4, 4e-8).
+// ex2.approx.ftz: a flushed denormal cannot change 1 + e.  The clamp keeps y finite (t < -88: sigmoid -> 1e-38 instead of
+// NaN from inf * 0).
 __device__ __forceinline__ float sigmoidf_fast(float t)
 {
-    float e, r;
+    float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * -1.4426950408889634f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    const float y = 1.0f + fminf(e, 1.0e38f);
+    float r = __int_as_float(0x7EF311C7 - __float_as_int(y));
+    r = r * fmaf(-y, r, 2.0f);
+    r = r * fmaf(-y, r, 2.0f);
+    r = r * fmaf(-y, r, 2.0f);
     return r;
 }
 

@@ -25,8 +25,11 @@ namespace yc {
 // 8 print clock64 wait statistics of CTA 0); the production instantiation carries none of that code.
 // AK: the feature maps are channels-last ([bs, H, W, K], e.g. the output of a channels-last RepConv): A is then a K-major
 // operand, one {64 k, 128 px} TMA box per stage, instead of the MN-major operand NCHW maps give.
-template <int BK, bool DBG, bool AK>
-__global__ void __maxnreg__(TC_MAX_REGS)
+// FUSED: the fused step (epilogue emits NMS candidates; capped at TC_MAX_REGS registers so that the NMS kernels of the
+// previous batch fit beside it); otherwise the z / raw writing forward, which keeps up to 64 accumulator values of a
+// half row in registers next to the sigmoids in flight and gets the whole register file (512 threads x 128).
+template <int BK, bool DBG, bool AK, bool FUSED>
+__global__ void __maxnreg__(FUSED ? TC_MAX_REGS : 128)
 head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
     constexpr int TC_BK = BK;
@@ -42,7 +45,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int n_stages = P.stages;
     float *slabs = (float *)(smem + n_stages * TC_STAGE_BYTES);
     const int n_epi_warps = P.epi_warps;
-    const int n_slabs = P.ibin ? 4 : n_epi_warps;   // IBin: one slab per TMEM lane quadrant, shared by its three warps
+    const int n_slabs = (P.ibin && !P.half_off) ? 4 : n_epi_warps;   // whole-row IBin epilogue: one slab per TMEM lane quadrant, shared by its three warps
     float2 *sbtab = (float2 *)((uint8_t *)slabs + (size_t)n_slabs * P.slab_bytes);   // half-row epilogue: (scale, bias) of every level
     uint64_t *bars = (uint64_t *)(sbtab + P.tab_entries);
     uint64_t *full_bar = bars;                        // [TC_MAX_STAGES]
@@ -213,7 +216,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
             // fused mode: the (scale, bias) pairs this warp needs live in registers; they change with the level and,
             // when the anchors of a pixel block are separate tiles (na*no > 256 columns), with the anchor group
-            if (P.fused && !P.ibin && tc.lv * YC_MAX_ANCHORS + tc.g != cur_key) {
+            if (FUSED && !P.ibin && tc.lv * YC_MAX_ANCHORS + tc.g != cur_key) {
                 sbv = load_box_sb(sb, lane, P.nc);
                 cur_key = tc.lv * YC_MAX_ANCHORS + tc.g;
             }
@@ -227,14 +230,21 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 if (lane == 0) mbar_arrive(&tempty_bar[buf]);
                 continue;
             }
-            if (P.fused) {
+            if (FUSED) {
                 if (P.ibin) fused_epilogue_ibin(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane);
                 else fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane, sbv);
                 continue;
             }
+            if (P.half_off && P.ibin) {   // eight warps: (quadrant, half of its rows)
+                const int pass = e >> 2;
+                store_rows_half_ibin<22>(P, L, tc.b, prow0 + 16 * pass, nv - 16 * pass, ar, taddr + ((uint32_t)(16 * pass) << 16),
+                                         smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no), smem_addr(slab), smem_addr(bars + 16),
+                                         &tempty_bar[buf], lane);
+                continue;
+            }
             if (P.half_off) {
                 store_rows_half_any<false>(P, L, tc.b, prow0, nv, ar, taddr, smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no),
-                                           smem_addr(slab), &tempty_bar[buf], lane, prof ? pf : nullptr);
+                                           smem_addr(slab), smem_addr(bars + 16), &tempty_bar[buf], lane, prof ? pf : nullptr);
                 continue;
             }
             store_epilogue<false>(P, L, tc.b, tc.p0, tc.g, e, q, lane, tmem_base + (uint32_t)(buf * TC_MAX_N), (uint8_t *)slabs,
@@ -318,17 +328,20 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     for (int i = 0; i < d->nl; ++i) any_raw = any_raw || d->level[i].raw != nullptr;
     // z / raw rows by halves (store_rows_half): 16-row slabs and the (scale, bias) table in shared memory
     int half_off = (!fused && !ibin) ? half_off_for(d->no, na_tile) : 0;
+    // IBin by halves (store_rows_half_ibin<22>): the reference's 21 bins, box part and objectness inside the lower 64 columns
+    if (!fused && ibin && d->bin_count == 21 && d->no > 64 && d->no <= 128) half_off = 64;
     { const char *e = getenv("YC_TC_HALF"); if (e && atoi(e) == 0) half_off = 0; }   // experiments: the whole-row epilogue
     const int tab_entries = half_off ? d->nl * N : 0;
     if (tab_entries * 8 > 16 * 1024) half_off = 0;
     const uint32_t slab_bytes = fused ? (uint32_t)round_up(TC_QUEUE_ROWS * (d->no - 5) * 4, 16)
-                                : ibin ? (uint32_t)round_up(32 * no_out * 4 + (any_raw ? 32 * d->no * 4 : 0), 16)
+                                : ibin ? (half_off ? (uint32_t)round_up(16 * (any_raw ? d->no : no_out) * 4, 16)   // one slab, raw rows then z rows
+                                                   : (uint32_t)round_up(32 * no_out * 4 + (any_raw ? 32 * d->no * 4 : 0), 16))
                                        : (uint32_t)round_up((half_off ? 16 : 32) * d->no * 4, 16);
-    const int epi_warps = ibin ? (fused ? 4 : 12) : 4 * na_tile;   // fused IBin: one warp per quadrant (most rows stop at the objectness)
+    // fused IBin: one warp per quadrant (most rows stop at the objectness); by halves: two per quadrant; whole rows: three
+    const int epi_warps = ibin ? (fused ? 4 : half_off ? 8 : 12) : 4 * na_tile;
     // K=64 per stage: 4 stages in the fused mode (no z slabs in shared memory), 2 next to the slabs.
-    // (K=128 x 2 stages measured 6 us slower on the C2 batch; YC_TC_BK overrides for experiments.)
+    // (K=128 x 2 stages measured 6 us slower on the C2 batch.)
     int bk = 64;
-    { const char *e = getenv("YC_TC_BK"); if (e && (atoi(e) == 64 || atoi(e) == 128)) bk = atoi(e); }
     // CTA pairs (cta_group::2) for the fused step: see yc_head_sm100_2cta.cu (measured 2-4 % faster than the 1-CTA
     // kernel for batches of 32 images and more: 8 feature-map stages instead of 4).  YC_TC_2CTA=0 keeps the 1-CTA kernel.
     // (r03) the z-writing forward takes the pair kernel too when its rows go by halves: per tile the 1-CTA kernel streams
@@ -339,7 +352,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     const int tile_px = pair ? 2 * TC_BM : TC_BM;
     const uint32_t b_slot_bytes = (uint32_t)round_up(npad * 64 * 2, 1024);   // npad is a multiple of 16: 2 KB steps
     const size_t stage_bytes = (size_t)TC_BM * bk * 2 + (size_t)(bk / 64) * b_slot_bytes;
-    const size_t fixed = 1024 + (size_t)(ibin ? 4 : 4 * na_tile) * slab_bytes + 256 +   // (fused IBin: 4 warps x one area each)
+    const size_t fixed = 1024 + (size_t)(ibin ? (half_off ? 8 : 4) : 4 * na_tile) * slab_bytes + 256 +   // (fused IBin: 4 warps x one area each)
                          (half_off ? (size_t)tab_entries * 8 : 0);
     int stages = TC_MAX_STAGES;
     while (stages > 2 && fixed + (size_t)stages * stage_bytes > 227 * 1024) --stages;
@@ -412,6 +425,14 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         L.n_groups = n_groups;
         L.bmap0 = s * n_groups;
         L.tile_begin = tiles;
+        {   // chunks of the tile order (n_groups > 1): a multiple of the grid, about 24 MB of feature maps, so that the
+            // second and third anchor group's pass over a chunk reads it from L2
+            const int sms = g_num_sms - g_reserved_sms > 0 ? g_num_sms - g_reserved_sms : 1;
+            const size_t tile_bytes = (size_t)lv.K * TC_BM * 2;
+            int m = (int)((size_t)(24u << 20) / ((size_t)sms * tile_bytes));
+            { const char *e = getenv("YC_TC_CHUNK"); if (e) m = atoi(e); }   // experiments (a huge value: group major over the whole level)
+            L.chunk_tiles = sms * (m < 1 ? 1 : m);
+        }
         L.row_off = row_off[i];
         L.stride = lv.stride;
         L.stride_y = lv.stride_y > 0.f ? lv.stride_y : lv.stride;
@@ -453,12 +474,12 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     const int grid = tiles < sms ? tiles : sms;
     const int threads = TC_NON_EPI_THREADS + 32 * epi_warps;
     void (*kern)(const TcMaps, const TcParams);
-    if (P.a_kmajor)
-        kern = P.debug ? (bk == 128 ? head_tc_kernel<128, true, true> : head_tc_kernel<64, true, true>)
-                       : (bk == 128 ? head_tc_kernel<128, false, true> : head_tc_kernel<64, false, true>);
+    if (P.fused)
+        kern = P.a_kmajor ? (P.debug ? head_tc_kernel<64, true, true, true> : head_tc_kernel<64, false, true, true>)
+                          : (P.debug ? head_tc_kernel<64, true, false, true> : head_tc_kernel<64, false, false, true>);
     else
-        kern = P.debug ? (bk == 128 ? head_tc_kernel<128, true, false> : head_tc_kernel<64, true, false>)
-                       : (bk == 128 ? head_tc_kernel<128, false, false> : head_tc_kernel<64, false, false>);
+        kern = P.a_kmajor ? (P.debug ? head_tc_kernel<64, true, true, false> : head_tc_kernel<64, false, true, false>)
+                          : (P.debug ? head_tc_kernel<64, true, false, false> : head_tc_kernel<64, false, false, false>);
     YC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kern<<<grid, threads, smem_bytes, stream>>>(maps, P);
     YC_CUDA(cudaGetLastError());

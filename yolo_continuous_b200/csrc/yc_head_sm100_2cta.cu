@@ -46,8 +46,9 @@ __device__ __forceinline__ void ring_advance(int &s, uint32_t &parity, int n, in
 }
 
 // AK: channels-last feature maps (A K-major): each 64-pixel box is one {64 k, 64 px} TMA box of the flat [bs*HW, K] view
-template <bool DBG, bool AK>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(TC_MAX_REGS)
+// FUSED: see head_tc_kernel (register cap of the fused step; the z-writing forward gets 128 registers)
+template <bool DBG, bool AK, bool FUSED>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(FUSED ? TC_MAX_REGS : 128)
 head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -265,7 +266,7 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
             const int nv = img < P.bs ? min(32, L.HW - prow0) : 0;
             const int ar = a;
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TC_MAX_N + a * P.no);
-            if (P.fused && tc.lv != cur_lv) { // one anchor group per tile, so `ar` is fixed for this warp
+            if (FUSED && tc.lv != cur_lv) { // one anchor group per tile, so `ar` is fixed for this warp
                 sbv = load_box_sb(L.sb + ar * P.no, lane, P.nc);
                 cur_lv = tc.lv;
             }
@@ -279,11 +280,11 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                 if (lane == 0) mbar_arrive_leader(&R.tempty[buf]);
                 continue;
             }
-            if (P.fused)
+            if (FUSED)
                 fused_epilogue<true>(P, L, img, prow0, nv, ar, taddr, slab, &R.tempty[buf], lane, sbv);
             else   // z / raw maps (the drop-in forward): rows by halves through the warp's 16-row slab
                 store_rows_half_any<true>(P, L, img, prow0, nv, ar, taddr, smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no),
-                                          smem_addr(slab), &R.tempty[buf], lane);
+                                          smem_addr(slab), smem_addr(bars + 40), &R.tempty[buf], lane);
             if (eprof) {
                 const long long e2 = clock64();
                 e_wait += e1 - e0;
@@ -295,7 +296,7 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
         if (eprof && lane == 0)
             printf("[yc prof2] epilogue warp %d: %d tiles, waiting tfull %lld, working %lld (max %lld per tile, %d tiles > 600)\n",
                    e, it, e_wait, e_work, e_max, e_slow);
-        if (!P.fused && lane == 0) bulk_wait_all0();   // global writes complete before the CTA exits
+        if (!FUSED && lane == 0) bulk_wait_all0();   // global writes complete before the CTA exits
     }
 
     tc_fence_before();
@@ -317,8 +318,13 @@ int launch_head_tc2(const TcMaps &maps, TcParams &P, int num_sms, cudaStream_t s
     const size_t smem_bytes = fixed + (size_t)stages * T2_A_BYTES;
     YC_REQUIRE(smem_bytes <= 227 * 1024, YC_ERR_UNSUPPORTED, "2-CTA head: needs %zu bytes of shared memory", smem_bytes);
     P.stages = stages;
-    void (*kern)(const TcMaps, const TcParams) = P.a_kmajor ? (P.debug ? head_tc2_kernel<true, true> : head_tc2_kernel<false, true>)
-                                                            : (P.debug ? head_tc2_kernel<true, false> : head_tc2_kernel<false, false>);
+    void (*kern)(const TcMaps, const TcParams);
+    if (P.fused)
+        kern = P.a_kmajor ? (P.debug ? head_tc2_kernel<true, true, true> : head_tc2_kernel<false, true, true>)
+                          : (P.debug ? head_tc2_kernel<true, false, true> : head_tc2_kernel<false, false, true>);
+    else
+        kern = P.a_kmajor ? (P.debug ? head_tc2_kernel<true, true, false> : head_tc2_kernel<false, true, false>)
+                          : (P.debug ? head_tc2_kernel<true, false, false> : head_tc2_kernel<false, false, false>);
     YC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int pairs = num_sms / 2;
     if (P.total_tiles < pairs) pairs = P.total_tiles;

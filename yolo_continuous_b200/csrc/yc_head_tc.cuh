@@ -46,6 +46,7 @@ struct TcLevel {
                         // level's box list, across image boundaries, so a 400-pixel P5 map wastes 12 % of a tile, not 28 %)
     int n_boxes;        // bs * boxes_per_img
     int tile_begin;     // first tile id of this level in schedule order
+    int chunk_tiles;    // n_groups > 1: pixel tiles per chunk of the tile order (see tile_coord_w)
     int row_off;        // first z row of this level
     float stride, stride_y;
     float anchor_wh[YC_MAX_ANCHORS * 2];
@@ -102,10 +103,16 @@ __device__ __forceinline__ TileCoord tile_coord_w(const TcParams &P, int t, int 
     TileCoord c;
     c.lv = l;
     c.g = 0;
-    if (P.lv[l].n_groups > 1) {   // group major: all pixel tiles of one anchor group are consecutive (weights stay put)
-        const int per_group = P.bs * P.lv[l].tiles_per_img;
-        c.g = r / per_group;
-        r -= c.g * per_group;
+    if (P.lv[l].n_groups > 1) {
+        // One anchor group per tile (IBin: 127 of 128 columns per anchor).  Group major inside CHUNKS of pixel tiles: a
+        // chunk's pixel tiles are walked once per anchor group, so a CTA keeps a group's weights for several tiles, and a
+        // chunk's feature maps (sized to stay in L2) come from HBM once instead of once per group.
+        const int n_px = P.bs * P.lv[l].tiles_per_img, ct = P.lv[l].chunk_tiles;
+        const int ch = r / (ct * P.lv[l].n_groups);
+        r -= ch * ct * P.lv[l].n_groups;
+        const int cs = min(ct, n_px - ch * ct);   // pixel tiles of this chunk (the last one may be short)
+        c.g = r / cs;
+        r = ch * ct + r - c.g * cs;
     }
     c.b = r / P.lv[l].tiles_per_img;
     c.p0 = (r - c.b * P.lv[l].tiles_per_img) * width;
@@ -575,14 +582,16 @@ __device__ __forceinline__ void half_slab_store(float *__restrict__ gdst, uint32
 //   PAIR    the TMEM-empty barrier lives in the pair's leader CTA
 template <int OFF, bool PAIR>
 __device__ __forceinline__ void store_rows_half(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar, uint32_t taddr,
-                                                uint32_t tab_s, uint32_t slab_s, uint64_t *tempty, int lane, long long *pf = nullptr)
+                                                uint32_t tab_s, uint32_t slab_s, uint32_t dummy_s, uint64_t *tempty, int lane, long long *pf = nullptr)
 {
     const int no = P.no;
     const int half = lane >> 4, r = lane & 15;
     const int cbase = half * OFF;                 // first column owned by this thread
     const float aw = L.anchor_wh[2 * ar], ah = L.anchor_wh[2 * ar + 1];
-    const uint32_t srow = slab_s + (uint32_t)(r * no + cbase) * 4u, trow = tab_s + (uint32_t)cbase * 8u;
-    const int ncols = half == 0 ? OFF : max(0, min(OFF, no - OFF));   // columns of this thread that exist (the rest: next anchor)
+    const uint32_t trow = tab_s + (uint32_t)cbase * 8u;
+    float *const srow = shared_f32(slab_s) + r * no + cbase;   // this thread's columns of its slab row
+    float *const dummy = shared_f32(dummy_s);                 // where the columns that do not exist (lanes 16-31: next anchor) go
+    const int ncols = half == 0 ? OFF : max(0, min(OFF, no - OFF));   // columns of this thread that exist
     long long c0_ = pf ? clock64() : 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
@@ -619,7 +628,7 @@ __device__ __forceinline__ void store_rows_half(const TcParams &P, const TcLevel
                 }
 #pragma unroll
                 for (int j = j0; j < j0 + HG && j < OFF; ++j)
-                    if (j < ncols) sts_f32(srow + 4u * j, w[j - j0]);
+                    *(j < ncols ? srow + j : dummy) = w[j - j0];
             }
             if (pf) { const long long c = clock64(); pf[1] += c - c0_; c0_ = c; }
             half_slab_store(L.raw + (((size_t)b * P.na_real + ar) * L.HW + grow) * no, slab_s, rows, no, lane);
@@ -647,12 +656,108 @@ __device__ __forceinline__ void store_rows_half(const TcParams &P, const TcLevel
                 }
 #pragma unroll
                 for (int j = j0; j < j0 + HG && j < OFF; ++j)
-                    if (j < ncols) sts_f32(srow + 4u * j, w[j - j0]);
+                    *(j < ncols ? srow + j : dummy) = w[j - j0];
             }
             if (pf) { const long long c = clock64(); pf[1] += c - c0_; c0_ = c; }
             half_slab_store(P.z + ((size_t)b * P.rows_total + L.row_off + (size_t)ar * L.HW + grow) * no, slab_s, rows, no, lane);
             if (pf) { const long long c = clock64(); pf[2] += c - c0_; c0_ = c; }
         }
+    }
+}
+
+// IBin rows by halves (nets/ibin.py:56-72, losses/sigmoid_bin.py:49-63): one anchor per tile, the accumulator row is
+// [x y | w: reg + bins | h: reg + bins | obj | cls] = no <= 128 columns, the z row [x y w h obj cls] = no - 2 LEN + 2.  EIGHT
+// epilogue warps: warp (quadrant q, pass) owns the 16 rows 32 q + 16 pass .. of the tile; lanes 0-15 hold the columns
+// [0, 64) of their row -- the whole box part and the objectness (2 + 2 LEN + 1 <= 64) -- and lanes 16-31 the columns
+// [64, 128), classes only.  One 64-register load, one wait, the TMEM buffer goes back, then 64 independent sigmoids per
+// thread; the bin arg-max (first maximum of the sigmoids, as torch.max) runs in registers of the lower half-warp.
+// The whole-row form (three warps per quadrant sharing the columns, 16-column chunks, branches on the column's role with
+// a run-time LEN) took 186-226 cycles per box column and warp (YC_TC_DEBUG bit 8).
+template <int LEN>
+__device__ __forceinline__ void store_rows_half_ibin(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar,
+                                                     uint32_t taddr, uint32_t tab_s, uint32_t slab_s, uint32_t dummy_s, uint64_t *tempty, int lane)
+{
+    constexpr int OFF = 64, C_OBJ = 2 + 2 * LEN, SHIFT = 2 * LEN - 2;   // z column = accumulator column - SHIFT from C_OBJ on
+    static_assert(C_OBJ < OFF, "box part and objectness must sit in the lower half");
+    const int no = P.no, no_out = P.no_out;
+    const int half = lane >> 4, r = lane & 15, cbase = half * OFF;
+    const int ncols = half == 0 ? OFF : max(0, min(OFF, no - OFF));
+    const uint32_t trow = tab_s + (uint32_t)cbase * 8u;
+    float *const dummy = shared_f32(dummy_s);
+    uint32_t v[OFF];
+    TmemLdHalf<64, OFF>::ld(taddr, v);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty);
+    const int rows = min(16, nv);
+    if (L.raw) {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        float *const srow = shared_f32(slab_s) + r * no + cbase;
+#pragma unroll
+        for (int j0 = 0; j0 < OFF; j0 += HG) {
+            float w[HG];
+#pragma unroll
+            for (int j = j0; j < j0 + HG; ++j) {
+                const float2 s_b = lds_f32x2(trow + 8u * j);
+                w[j - j0] = fmaf(__uint_as_float(v[j]), s_b.x, s_b.y);
+            }
+#pragma unroll
+            for (int j = j0; j < j0 + HG; ++j)
+                *(j < ncols ? srow + j : dummy) = w[j - j0];
+        }
+        half_slab_store(L.raw + (((size_t)b * P.na_real + ar) * L.HW + prow0) * no, slab_s, rows, no, lane);
+    }
+    if (P.write_z) {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        const int p = prow0 + r;
+        const float gx = (float)(p % L.nx), gy = (float)(p / L.nx);
+        float *const srow = shared_f32(slab_s) + r * no_out;   // this thread's z row
+        float *const scol = srow + (cbase - SHIFT);            // [j]: z column of accumulator column cbase + j
+        float reg_w = 0.f, reg_h = 0.f, best_w = -1.f, best_h = -1.f;
+        int idx_w = 0, idx_h = 0;
+#pragma unroll
+        for (int j0 = 0; j0 < OFF; j0 += HG) {
+            float w[HG];
+#pragma unroll
+            for (int j = j0; j < j0 + HG; ++j) {
+                const float2 s_b = lds_f32x2(trow + 8u * j);
+                w[j - j0] = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
+            }
+#pragma unroll
+            for (int j = j0; j < j0 + HG; ++j) {
+                const float sg = w[j - j0];
+                if (j < C_OBJ) {
+                    // lower half: box part (kept in registers); upper half: a class column
+                    if (j == 2) reg_w = sg;
+                    else if (j > 2 && j < 2 + LEN) { if (sg > best_w) { best_w = sg; idx_w = j - 3; } }
+                    else if (j == 2 + LEN) reg_h = sg;
+                    else if (j > 2 + LEN) { if (sg > best_h) { best_h = sg; idx_h = j - 3 - LEN; } }
+                    if (j < 2) {   // lower half: decoded x / y at z column j; upper half: a class
+                        const float d = j == 0 ? decode_xy(sg, gx, L.stride) : decode_xy(sg, gy, L.stride_y);
+                        *(half == 0 ? srow + j : (j < ncols ? scol + j : dummy)) = half == 0 ? d : sg;
+                    } else {
+                        *(half != 0 && j < ncols ? scol + j : dummy) = sg;
+                    }
+                } else {
+                    *(j < ncols ? scol + j : dummy) = sg;
+                }
+            }
+        }
+        if (half == 0) {   // (reg * 2 - 1) * step + bins[argmax], clamped to [0, 4], times the anchor
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                float t = __fmul_rn(d == 0 ? reg_w : reg_h, 2.0f);
+                t = __fadd_rn(t, -1.0f);
+                t = __fmul_rn(t, P.bin_step);
+                float res = __fadd_rn(t, __ldg(P.bins + (d == 0 ? idx_w : idx_h)));
+                res = fminf(fmaxf(res, 0.0f), 4.0f);
+                srow[2 + d] = __fmul_rn(res, L.anchor_wh[2 * ar + d]);
+            }
+        }
+        half_slab_store(P.z + ((size_t)b * P.rows_total + L.row_off + (size_t)ar * L.HW + prow0) * no_out, slab_s, rows, no_out, lane);
     }
 }
 
@@ -668,15 +773,15 @@ __host__ __device__ inline int half_off_for(int no, int na_tile)
 
 template <bool PAIR>
 __device__ __forceinline__ void store_rows_half_any(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar, uint32_t taddr,
-                                                    uint32_t tab_s, uint32_t slab_s, uint64_t *tempty, int lane, long long *pf = nullptr)
+                                                    uint32_t tab_s, uint32_t slab_s, uint32_t dummy_s, uint64_t *tempty, int lane, long long *pf = nullptr)
 {
     switch (P.half_off) {
-    case 4: store_rows_half<4, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
-    case 8: store_rows_half<8, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
-    case 16: store_rows_half<16, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
-    case 32: store_rows_half<32, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
-    case 43: store_rows_half<43, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
-    default: store_rows_half<64, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, tempty, lane, pf); break;
+    case 4: store_rows_half<4, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, dummy_s, tempty, lane, pf); break;
+    case 8: store_rows_half<8, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, dummy_s, tempty, lane, pf); break;
+    case 16: store_rows_half<16, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, dummy_s, tempty, lane, pf); break;
+    case 32: store_rows_half<32, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, dummy_s, tempty, lane, pf); break;
+    case 43: store_rows_half<43, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, dummy_s, tempty, lane, pf); break;
+    default: store_rows_half<64, PAIR>(P, L, b, prow0, nv, ar, taddr, tab_s, slab_s, dummy_s, tempty, lane, pf); break;
     }
 }
 

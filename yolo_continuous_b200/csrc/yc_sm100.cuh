@@ -77,6 +77,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 // shared memory by 32-bit shared-window address (pointers derived from the dynamic shared array through integer
 // arithmetic lose their address space and compile to generic LD / ST)
 __device__ __forceinline__ void sts_f32(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+// A pointer the compiler KNOWS to be shared memory (dynamic shared array + byte offset): plain C++ stores through it
+// compile to st.shared and, unlike volatile asm statements, may be scheduled freely among the arithmetic.
+__device__ __forceinline__ float *shared_f32(uint32_t saddr)
+{
+    extern __shared__ uint8_t yc_dyn_smem[];
+    return (float *)(yc_dyn_smem + (saddr - smem_addr(yc_dyn_smem)));
+}
+// predicated form: the value is computed by every thread (a C++ `if` around the store lets the compiler sink the whole
+// computation of the value into a divergent branch per column, which serialises the columns)
+__device__ __forceinline__ void sts_f32_if(uint32_t saddr, float v, bool on)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}" ::"r"(saddr), "f"(v), "r"((uint32_t)on) : "memory");
+}
 __device__ __forceinline__ float2 lds_f32x2(uint32_t saddr)
 {
     float2 v;
