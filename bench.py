@@ -324,6 +324,24 @@ def other_configs(dev, peaks):
                                   "frac": byts / (ms / 1e3) / hbm, "tensor_tflops": flops / (ms / 1e3) / 1e12}}
         del xs, z
         torch.cuda.empty_cache()
+    # C2 through the drop-in forward that materialises z (what IDetect.forward returns to a reference user): S1, bf16 maps,
+    # z only and with the raw maps list (the reference's return value, twice the output bytes)
+    head = make_head().to(dev)
+    xs = make_maps(64, 1234, torch.bfloat16, dev)
+    s1 = {}
+    for name, raw in (("z_only", False), ("z_and_raw_maps", True)):
+        head.return_raw = raw
+        with torch.no_grad():
+            ms_f = timed_gpu(lambda: head(list(xs)), 20, 3)
+        byts = (BYTES_PER_IMG["bf16"] + (25200 * 85 * 4 if raw else 0)) * 64
+        s1[name] = {"forward_ms": ms_f, "images_per_s": 64 / ms_f * 1e3,
+                    "roofline": {"bound": "hbm", "achieved": byts / (ms_f / 1e3) / 1e9, "peak": hbm / 1e9, "unit": "GB/s",
+                                 "frac": byts / (ms_f / 1e3) / hbm, "bytes": byts}}
+    out["c2_forward_z_bf16_bs64"] = dict(s1, config="C2, IDetect.forward -> z [64, 25200, 85] float32 from bf16 maps (S1: 14.30 MB/img; "
+                                         "with the raw maps 22.87 MB/img), module call incl. allocation; head_tc2_kernel, rows by halves",
+                                         kernel="head_tc2_kernel<FUSED=false> (CTA pairs, z rows by halves through 16-row slabs)")
+    del xs
+    torch.cuda.empty_cache()
     # C2 with float32 feature maps (the reference's own precision, 1e-5 parity): drop-in forward and head -> NMS
     head = make_head().to(dev)
     xs = make_maps(64, 1234, torch.float32, dev)

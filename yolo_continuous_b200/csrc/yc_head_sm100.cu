@@ -231,6 +231,12 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 continue;
             }
             if (FUSED) {
+                if (P.ibin && P.half_off) {   // eight warps: (quadrant, half of its rows)
+                    const int pass16 = e >> 2;
+                    fused_epilogue_ibin_half<22>(P, L, tc.b, prow0 + 16 * pass16, nv - 16 * pass16, ar, taddr, pass16,
+                                                 smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no), &tempty_bar[buf], lane);
+                    continue;
+                }
                 if (P.ibin) fused_epilogue_ibin(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane);
                 else fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane, sbv);
                 continue;
@@ -329,7 +335,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     // z / raw rows by halves (store_rows_half): 16-row slabs and the (scale, bias) table in shared memory
     int half_off = (!fused && !ibin) ? half_off_for(d->no, na_tile) : 0;
     // IBin by halves (store_rows_half_ibin<22>): the reference's 21 bins, box part and objectness inside the lower 64 columns
-    if (!fused && ibin && d->bin_count == 21 && d->no > 64 && d->no <= 128) half_off = 64;
+    if (ibin && d->bin_count == 21 && d->no > 64 && d->no <= 128) half_off = 64;   // (the fused step too: fused_epilogue_ibin_half)
     { const char *e = getenv("YC_TC_HALF"); if (e && atoi(e) == 0) half_off = 0; }   // experiments: the whole-row epilogue
     const int tab_entries = half_off ? d->nl * N : 0;
     if (tab_entries * 8 > 16 * 1024) half_off = 0;
@@ -338,7 +344,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
                                                    : (uint32_t)round_up(32 * no_out * 4 + (any_raw ? 32 * d->no * 4 : 0), 16))
                                        : (uint32_t)round_up((half_off ? 16 : 32) * d->no * 4, 16);
     // fused IBin: one warp per quadrant (most rows stop at the objectness); by halves: two per quadrant; whole rows: three
-    const int epi_warps = ibin ? (fused ? 4 : half_off ? 8 : 12) : 4 * na_tile;
+    const int epi_warps = ibin ? (half_off ? 8 : fused ? 4 : 12) : 4 * na_tile;
     // K=64 per stage: 4 stages in the fused mode (no z slabs in shared memory), 2 next to the slabs.
     // (K=128 x 2 stages measured 6 us slower on the C2 batch.)
     int bk = 64;
