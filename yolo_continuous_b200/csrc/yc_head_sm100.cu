@@ -410,6 +410,10 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     P.half_off = half_off;
     P.tab_entries = half_off ? n * N : 0;   // levels in schedule order (those that meet the TMA rules)
     { const char *e = getenv("YC_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
+    // feature maps are read once: in the fused step their loads carry the L2 evict-first policy (A/B on one box: 79.0 / 79.3
+    // -> 78.3 / 78.4 us per C2 batch; the z-writing forward measured no gain and keeps the default policy)
+    P.a_hint = fused ? 1 : 0;
+    { const char *e = getenv("YC_TC_AHINT"); if (e) P.a_hint = atoi(e); }
     if (fused) {
         P.fused = 1; P.nc = fused->nc; P.conf = fused->conf; P.div_w = fused->div_w; P.div_h = fused->div_h;
         P.ws = fused->ws;

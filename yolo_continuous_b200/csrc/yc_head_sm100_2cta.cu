@@ -115,6 +115,7 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
         // ===================== feature-map (A) producer, both CTAs =====================
         int sa = 0;
         uint32_t pa = 0;
+        const uint64_t pol = l2_policy_evict_first();
         for (int t = pair; t < P.total_tiles; t += n_pairs) {
             const BoxTile tc = box_tile(P, t);
             const int nkb = (P.lv[tc.lv].K + T2_BK - 1) / T2_BK;
@@ -134,6 +135,9 @@ head_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
                             const int HW = P.lv[tc.lv].HW;
                             tma_load_2d_pair(dst, ma, &R.a_full[sa], kb * T2_BK, b0 * HW + p0);
                             tma_load_2d_pair(dst + T2_A_BYTES / 2, ma, &R.a_full[sa], kb * T2_BK, b1 * HW + p1);
+                        } else if (P.a_hint) {
+                            tma_load_3d_pair_hint(dst, ma, &R.a_full[sa], p0, kb * T2_BK, b0, pol);
+                            tma_load_3d_pair_hint(dst + T2_A_BYTES / 2, ma, &R.a_full[sa], p1, kb * T2_BK, b1, pol);
                         } else {
                             tma_load_3d_pair(dst, ma, &R.a_full[sa], p0, kb * T2_BK, b0);
                             tma_load_3d_pair(dst + T2_A_BYTES / 2, ma, &R.a_full[sa], p1, kb * T2_BK, b1);

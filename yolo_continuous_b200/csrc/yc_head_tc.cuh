@@ -75,6 +75,7 @@ struct TcParams {
     int debug;                 // YC_TC_DEBUG bits (timing experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA,
                                // 128 z epilogue without the TMEM reads / decode (stores only), 256 without the stores
     int stages;                // depth of the smem ring
+    int a_hint;                // 1 = feature-map loads carry the L2 evict-first policy (CTA-pair kernel; YC_TC_AHINT overrides)
     int half_off;              // > 0: z / raw rows are produced by halves (store_rows_half<half_off>), see there
     int tab_entries;           // (scale, bias) pairs staged in shared memory: n_lv * na_real * no (half-row epilogue)
     int a_kmajor;              // feature maps are channels-last: A is a K-major operand

@@ -202,6 +202,21 @@ __device__ __forceinline__ void tma_load_3d_pair(void *dst, const CUtensorMap *m
         "l"(m), "r"(smem_addr(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// L2 eviction policies for streamed data (read or written once)
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_3d_pair_hint(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], "
+        "[%2], %6;" ::"r"(smem_addr(dst)),
+        "l"(m), "r"(smem_addr(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t ncols)
 {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(ncols)
