@@ -429,6 +429,35 @@ def test_tcgen05_head_vs_oracle_bf16(kind):
         assert torch.equal(tr[i], raws[i])
 
 
+@pytest.mark.parametrize("nc", [2, 9, 20, 50, 81, 100, 123])
+def test_tcgen05_half_row_epilogue_class_counts(nc, monkeypatch):
+    """The z / raw epilogue that works by half rows takes its half-split offset from a small set (4, 8, 16, 32, 43, 64):
+    class counts that land on each of them -- no = 7, 14, 25, 55 (all anchors in one tile), 86 and 105 (one anchor per
+    tile), 128 (a full 2 x 64 row) -- on ragged maps and an odd batch, against the oracle on the same bf16 inputs, on the
+    CTA-pair kernel and on the 1-CTA kernel, z with and without the raw maps."""
+    from yolo_continuous_b200 import _lib
+    ch, shapes = (64, 128, 256), [(12, 20), (6, 12), (4, 6)]
+    head, xs = _random_head_case("idetect", nc, ch, shapes, 3, 30 + nc, torch.bfloat16)
+    p = _oracle_params(head, "idetect", True)
+    z_ref, raw_ref = orc.head_forward("idetect", p, [x.float().numpy() for x in xs], [8.0, 16.0, 32.0])
+    head = head.to(DEV)
+    head.head_path = _lib.YC_PATH_TCGEN05
+    scale = box_scale(p["anchors"], [8.0, 16.0, 32.0], shapes, head.na, nc + 5)
+    outs = []
+    for two_cta in ("1", "0"):
+        monkeypatch.setenv("YC_TC_2CTA", two_cta)
+        head.return_raw = True
+        z, raws = head([x.to(DEV) for x in xs])
+        assert_close_scaled(z.cpu().numpy(), z_ref, scale, 1e-4, f"half rows nc={nc} 2cta={two_cta}")
+        for i in range(head.nl):
+            np.testing.assert_allclose(raws[i].cpu().numpy(), raw_ref[i], rtol=0, atol=1e-4)
+        head.return_raw = False
+        z_only, _ = head([x.to(DEV) for x in xs])
+        assert torch.equal(z_only, z)
+        outs.append(z)
+    assert torch.equal(outs[0], outs[1])    # same accumulation order on both kernels
+
+
 def test_fp32_maps_bf16_switch_matches_bf16_inputs():
     """head.fp32_maps = "bf16": float32 maps are cast and take the tcgen05 kernel -- same result as passing bf16 maps."""
     from yolo_continuous_b200.nets import IDetect
