@@ -921,7 +921,7 @@ __device__ __forceinline__ void fused_epilogue(const TcParams &P, const TcLevel 
         // then scan the classes with the 32 lanes spread over the classes.
         int base = 0;
         if (lane == 0) base = atomicAdd(&P.ws.cand_count[b], n_surv);
-        float *q = slab; // per-warp queue [TC_QUEUE_ROWS][nc]
+        float *q = shared_f32(smem_addr(slab)); // per-warp queue [TC_QUEUE_ROWS][nc] (a pointer the compiler knows to be shared)
         const int nc = P.nc;
         float *qrow = q + __popc(surv & ((1u << lane) - 1u)) * nc;
         switch ((nc & 15) == 0 ? nc >> 4 : 0) {

@@ -23,9 +23,10 @@ class HeadBase(nn.Module):
     export = False  # nets/idetect.py:9
     head_path = _lib.YC_PATH_AUTO   # which kernel family runs the conv (see include/yc_b200.h)
     return_raw = True               # eval forward returns (z, raw list) as the reference does
-    # float32 feature maps run the exact FFMA kernel (1e-5 parity, ~27 TFLOP/s).  "bf16" casts them to bfloat16 first
-    # and takes the tcgen05 kernel (1e-3 parity, the precision class of the TF32 convolutions torch uses on a GPU by
-    # default, ~10x faster end to end); bfloat16 maps always take the tcgen05 kernel.
+    # float32 feature maps keep float32 grade ("exact", 1e-5 parity): the tensor-core kernel that splits both operands into
+    # fp16 hi/lo parts (head_tcs_kernel), or the FFMA kernel on the generic path.  "bf16" casts them to bfloat16 first and
+    # takes the bf16 tcgen05 kernels (1e-3 parity, the precision class of the TF32 convolutions torch uses on a GPU by
+    # default, ~3x faster); bfloat16 maps always take the bf16 tcgen05 kernels.
     fp32_maps = "exact"
 
     def _init_common(self, nc, anchors, no):

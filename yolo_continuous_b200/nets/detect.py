@@ -2,7 +2,7 @@
 
 This is the head the shipped YAMLs use (Variant A).  `forward` keeps the reference
 contract (raw conv maps, torch convolutions).  `forward_decoded` is the B200 path for inference: the same
-fused kernel as IDetect (1x1 conv as a tcgen05 GEMM for bf16 maps / exact FFMA for fp32 maps, sigmoid and
+fused kernel as IDetect (1x1 conv as a tcgen05 GEMM: bf16 maps directly, fp32 maps through the fp16 hi/lo split, sigmoid and
 box decode in the epilogue) with Variant A's normalised-box decode -- it returns what
 `decode_box(self(x), anchors, anchors_mask, num_classes, image_size)` returns (detect.py:29-87) without ever
 materialising the raw maps.
