@@ -28,7 +28,9 @@ namespace yc {
 // FUSED: the fused step (epilogue emits NMS candidates; capped at TC_MAX_REGS registers so that the NMS kernels of the
 // previous batch fit beside it); otherwise the z / raw writing forward, which keeps up to 64 accumulator values of a
 // half row in registers next to the sigmoids in flight and gets the whole register file (512 threads x 128).
-template <int BK, bool DBG, bool AK, bool FUSED>
+// IBIN: the IBin head; a separate instantiation so that its 64-register half-row loads do not weigh on the register
+// allocation of the other heads' epilogues.
+template <int BK, bool DBG, bool AK, bool FUSED, bool IBIN>
 __global__ void __maxnreg__(FUSED ? TC_MAX_REGS : 128)
 head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams P)
 {
@@ -45,7 +47,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int n_stages = P.stages;
     float *slabs = (float *)(smem + n_stages * TC_STAGE_BYTES);
     const int n_epi_warps = P.epi_warps;
-    const int n_slabs = (P.ibin && !P.half_off) ? 4 : n_epi_warps;   // whole-row IBin epilogue: one slab per TMEM lane quadrant, shared by its three warps
+    const int n_slabs = (IBIN && !P.half_off) ? 4 : n_epi_warps;   // whole-row IBin epilogue: one slab per TMEM lane quadrant, shared by its three warps
     float2 *sbtab = (float2 *)((uint8_t *)slabs + (size_t)n_slabs * P.slab_bytes);   // half-row epilogue: (scale, bias) of every level
     uint64_t *bars = (uint64_t *)(sbtab + P.tab_entries);
     uint64_t *full_bar = bars;                        // [TC_MAX_STAGES]
@@ -199,7 +201,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // ===================== epilogue: TMEM -> sigmoid/decode -> slab -> bulk store =====================
         const int e = warp - TC_NON_EPI_THREADS / 32;
         const int q = warp & 3;     // TMEM lane quadrant this warp may read
-        const int a = P.ibin ? 0 : e >> 2;       // anchor of the tile handled by this warp (IBin: one anchor per tile)
+        const int a = IBIN ? 0 : e >> 2;         // anchor of the tile handled by this warp (IBin: one anchor per tile)
         float *slab = (float *)((uint8_t *)slabs + (size_t)e * P.slab_bytes);
         int it = 0, cur_key = -1;
         BoxSb sbv;
@@ -216,7 +218,7 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 
             // fused mode: the (scale, bias) pairs this warp needs live in registers; they change with the level and,
             // when the anchors of a pixel block are separate tiles (na*no > 256 columns), with the anchor group
-            if (FUSED && !P.ibin && tc.lv * YC_MAX_ANCHORS + tc.g != cur_key) {
+            if (FUSED && !IBIN && tc.lv * YC_MAX_ANCHORS + tc.g != cur_key) {
                 sbv = load_box_sb(sb, lane, P.nc);
                 cur_key = tc.lv * YC_MAX_ANCHORS + tc.g;
             }
@@ -231,24 +233,24 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                 continue;
             }
             if (FUSED) {
-                if (P.ibin && P.half_off) {   // eight warps: (quadrant, half of its rows)
+                if (IBIN && P.half_off) {   // eight warps: (quadrant, half of its rows)
                     const int pass16 = e >> 2;
-                    fused_epilogue_ibin_half<22>(P, L, tc.b, prow0 + 16 * pass16, nv - 16 * pass16, ar, taddr, pass16,
-                                                 smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no), &tempty_bar[buf], lane);
+                    fused_epilogue_ibin_half<22, false>(P, L, tc.b, prow0 + 16 * pass16, nv - 16 * pass16, ar, taddr, pass16,
+                                                 smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no), smem_addr(slab), &tempty_bar[buf], lane);
                     continue;
                 }
-                if (P.ibin) fused_epilogue_ibin(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane);
+                if (IBIN) fused_epilogue_ibin(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane);
                 else fused_epilogue<false>(P, L, tc.b, prow0, nv, ar, taddr, slab, &tempty_bar[buf], lane, sbv);
                 continue;
             }
-            if (P.half_off && P.ibin) {   // eight warps: (quadrant, half of its rows)
+            if (IBIN && P.half_off) {   // eight warps: (quadrant, half of its rows)
                 const int pass = e >> 2;
-                store_rows_half_ibin<22>(P, L, tc.b, prow0 + 16 * pass, nv - 16 * pass, ar, taddr + ((uint32_t)(16 * pass) << 16),
+                store_rows_half_ibin<22, false>(P, L, tc.b, prow0 + 16 * pass, nv - 16 * pass, ar, taddr + ((uint32_t)(16 * pass) << 16),
                                          smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no), smem_addr(slab), smem_addr(bars + 16),
                                          &tempty_bar[buf], lane);
                 continue;
             }
-            if (P.half_off) {
+            if (!IBIN && P.half_off) {
                 store_rows_half_any<false>(P, L, tc.b, prow0, nv, ar, taddr, smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no),
                                            smem_addr(slab), smem_addr(bars + 16), &tempty_bar[buf], lane, prof ? pf : nullptr);
                 continue;
@@ -298,6 +300,7 @@ int set_reserved_sms(int n)
 }
 
 int launch_head_tc2(const TcMaps &maps, TcParams &P, int num_sms, cudaStream_t stream); // yc_head_sm100_2cta.cu
+int launch_head_tc2i(const TcMaps &maps, TcParams &P, int num_sms, cudaStream_t stream); // yc_head_sm100_2cta_ibin.cu
 int launch_head_split(const yc_head_desc *d, int rows_total, const int *row_off, unsigned *left_mask, void *enc_fn, int num_sms,
                       cudaStream_t stream);                                              // yc_head_sm100_split.cu
 
@@ -339,7 +342,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     { const char *e = getenv("YC_TC_HALF"); if (e && atoi(e) == 0) half_off = 0; }   // experiments: the whole-row epilogue
     const int tab_entries = half_off ? d->nl * N : 0;
     if (tab_entries * 8 > 16 * 1024) half_off = 0;
-    const uint32_t slab_bytes = fused ? (uint32_t)round_up(TC_QUEUE_ROWS * (d->no - 5) * 4, 16)
+    const uint32_t slab_bytes = fused ? ((ibin && half_off) ? 512u : (uint32_t)round_up(TC_QUEUE_ROWS * (d->no - 5) * 4, 16))   // (fused IBin by halves: one 128-float row buffer per warp)
                                 : ibin ? (half_off ? (uint32_t)round_up(16 * (any_raw ? d->no : no_out) * 4, 16)   // one slab, raw rows then z rows
                                                    : (uint32_t)round_up(32 * no_out * 4 + (any_raw ? 32 * d->no * 4 : 0), 16))
                                        : (uint32_t)round_up((half_off ? 16 : 32) * d->no * 4, 16);
@@ -353,6 +356,10 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     // (r03) the z-writing forward takes the pair kernel too when its rows go by halves: per tile the 1-CTA kernel streams
     // all of W from L2 (777 MB per C2 batch next to 367 MB of maps) through a ring that the slabs leave 2-3 stages deep
     bool pair = (fused != nullptr || half_off > 0) && n_groups == 1 && npad % 16 == 0;
+    // IBin by half rows, NCHW maps: the CTA-pair kernel that reads the maps once per pixel tile for all anchors
+    // (yc_head_sm100_2cta_ibin.cu; YC_TC_2CTA=0 keeps the 1-CTA kernel, one (pixel tile, anchor) per tile)
+    const bool ibin_pair_ok = ibin && half_off > 0 && !d->x_channels_last && d->na <= 4;
+    if (ibin_pair_ok) pair = true;
     { const char *e = getenv("YC_TC_2CTA"); if (e && atoi(e) == 0) pair = false; }
     if (pair) bk = T2_BK; // feature-map box height of the CTA-pair kernel
     const int tile_px = pair ? 2 * TC_BM : TC_BM;
@@ -447,7 +454,7 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
         L.stride = lv.stride;
         L.stride_y = lv.stride_y > 0.f ? lv.stride_y : lv.stride;
         for (int j = 0; j < YC_MAX_ANCHORS * 2; ++j) L.anchor_wh[j] = lv.anchor_wh[j];
-        tiles += pair ? (L.n_boxes + 3) / 4 : d->bs * L.tiles_per_img * n_groups;
+        tiles += pair ? (L.n_boxes + 3) / 4 : d->bs * L.tiles_per_img * n_groups;   // (pair + IBin: a tile holds all anchors)
         if (d->x_channels_last) {   // A: X [bs*HW, K] bf16 (channels-last), box {64 k, 128 px} (pair kernel: 64 px)
             cuuint64_t gdim[2] = {(cuuint64_t)lv.K, (cuuint64_t)d->bs * HW};
             cuuint64_t gstr[1] = {(cuuint64_t)lv.K * 2};
@@ -479,17 +486,21 @@ int launch_head_tcgen05(const yc_head_desc *d, int rows_total, const int *row_of
     }
     P.total_tiles = tiles;
 
+    if (pair && ibin) return launch_head_tc2i(maps, P, g_num_sms - g_reserved_sms > 1 ? g_num_sms - g_reserved_sms : 2, stream);
     if (pair) return launch_head_tc2(maps, P, g_num_sms - g_reserved_sms > 1 ? g_num_sms - g_reserved_sms : 2, stream);
     const int sms = g_num_sms - g_reserved_sms > 0 ? g_num_sms - g_reserved_sms : 1;
     const int grid = tiles < sms ? tiles : sms;
     const int threads = TC_NON_EPI_THREADS + 32 * epi_warps;
+    // (the YC_TC_DEBUG instantiations exist for NCHW maps only)
     void (*kern)(const TcMaps, const TcParams);
-    if (P.fused)
-        kern = P.a_kmajor ? (P.debug ? head_tc_kernel<64, true, true, true> : head_tc_kernel<64, false, true, true>)
-                          : (P.debug ? head_tc_kernel<64, true, false, true> : head_tc_kernel<64, false, false, true>);
-    else
-        kern = P.a_kmajor ? (P.debug ? head_tc_kernel<64, true, true, false> : head_tc_kernel<64, false, true, false>)
-                          : (P.debug ? head_tc_kernel<64, true, false, false> : head_tc_kernel<64, false, false, false>);
+    const bool dbg = P.debug && !P.a_kmajor;
+    if (ibin) {
+        if (P.fused) kern = P.a_kmajor ? head_tc_kernel<64, false, true, true, true> : dbg ? head_tc_kernel<64, true, false, true, true> : head_tc_kernel<64, false, false, true, true>;
+        else kern = P.a_kmajor ? head_tc_kernel<64, false, true, false, true> : dbg ? head_tc_kernel<64, true, false, false, true> : head_tc_kernel<64, false, false, false, true>;
+    } else {
+        if (P.fused) kern = P.a_kmajor ? head_tc_kernel<64, false, true, true, false> : dbg ? head_tc_kernel<64, true, false, true, false> : head_tc_kernel<64, false, false, true, false>;
+        else kern = P.a_kmajor ? head_tc_kernel<64, false, true, false, false> : dbg ? head_tc_kernel<64, true, false, false, false> : head_tc_kernel<64, false, false, false, false>;
+    }
     YC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kern<<<grid, threads, smem_bytes, stream>>>(maps, P);
     YC_CUDA(cudaGetLastError());

@@ -122,7 +122,7 @@ __device__ __forceinline__ TileCoord tile_coord_w(const TcParams &P, int t, int 
 
 __device__ __forceinline__ TileCoord tile_coord(const TcParams &P, int t) { return tile_coord_w(P, t, TC_BM); }
 
-// CTA-pair kernel: tile id -> (level, first 64-pixel box of the tile in the level's flat box list)
+// CTA-pair kernels: tile id -> (level, first 64-pixel box of the tile in the level's flat box list)
 struct BoxTile { int lv, j0; };
 __device__ __forceinline__ BoxTile box_tile(const TcParams &P, int t)
 {
@@ -674,7 +674,7 @@ __device__ __forceinline__ void store_rows_half(const TcParams &P, const TcLevel
 // thread; the bin arg-max (first maximum of the sigmoids, as torch.max) runs in registers of the lower half-warp.
 // The whole-row form (three warps per quadrant sharing the columns, 16-column chunks, branches on the column's role with
 // a run-time LEN) took 186-226 cycles per box column and warp (YC_TC_DEBUG bit 8).
-template <int LEN>
+template <int LEN, bool PAIR>
 __device__ __forceinline__ void store_rows_half_ibin(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar,
                                                      uint32_t taddr, uint32_t tab_s, uint32_t slab_s, uint32_t dummy_s, uint64_t *tempty, int lane)
 {
@@ -690,7 +690,10 @@ __device__ __forceinline__ void store_rows_half_ibin(const TcParams &P, const Tc
     tmem_ld_wait();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty);
+    if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(tempty);
+        else mbar_arrive(tempty);
+    }
     const int rows = min(16, nv);
     if (L.raw) {
         if (lane == 0) bulk_wait_read0();
@@ -770,22 +773,51 @@ __device__ __forceinline__ void store_rows_half_ibin(const TcParams &P, const Tc
 // threshold nearly every second tile has such a warp (measured: 392 us per 16 images at 1280x1280 against 160 us with
 // the epilogue switched off).  Lanes 0-15 own the box part, the objectness and the first classes of their row, lanes 16-31
 // the remaining classes of the same row; the class maximum is combined with one shuffle (first maximum, as torch.max).
+// survivors of the objectness test among this warp's 16 rows, from the objectness accumulator of the quadrant's 32 rows
+// (lane = row, already loaded): class scores are sigmoids (<= 1), so obj >= conf is necessary for obj * cls >= conf
 template <int LEN>
-__device__ __forceinline__ void fused_epilogue_ibin_half(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar,
-                                                         uint32_t tq, int pass16, uint32_t tab_s, uint64_t *tempty, int lane)
+__device__ __forceinline__ unsigned ibin_obj_survivors(uint32_t o_raw, uint32_t tab_s, int pass16, int nv, float conf, int lane)
 {
-    constexpr int OFF = 64, C_OBJ = 2 + 2 * LEN, C_CLS = C_OBJ + 1;
-    const int no = P.no;
-    const int half = lane >> 4, r = lane & 15, cbase = half * OFF;
-    const int ncols = half == 0 ? OFF : max(0, min(OFF, no - OFF));
+    const float2 so = lds_f32x2(tab_s + 8u * (2 + 2 * LEN));
+    const float obj32 = sigmoidf_fast(fmaf(__uint_as_float(o_raw), so.x, so.y));
+    const bool mine = (lane >> 4) == pass16 && (lane & 15) < nv;
+    return __ballot_sync(0xffffffffu, mine && obj32 >= conf);
+}
+
+template <int LEN, bool PAIR>
+__device__ __forceinline__ void fused_epilogue_ibin_half_tail(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar,
+                                                              uint32_t tq, int pass16, uint32_t tab_s, uint32_t qrow_s, uint64_t *tempty,
+                                                              int lane, unsigned surv);
+
+template <int LEN, bool PAIR>
+__device__ __forceinline__ void fused_epilogue_ibin_half(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar,
+                                                         uint32_t tq, int pass16, uint32_t tab_s, uint32_t qrow_s, uint64_t *tempty,
+                                                         int lane)
+{
     // objectness of the quadrant's 32 rows (lane = row); this warp looks at its own 16
     uint32_t o1[1];
-    TmemLd<1>::ld(tq + (uint32_t)C_OBJ, o1);
+    TmemLd<1>::ld(tq + (uint32_t)(2 + 2 * LEN), o1);
     tmem_ld_wait();
-    const float2 so = lds_f32x2(tab_s + 8u * C_OBJ);
-    const float obj32 = sigmoidf_fast(fmaf(__uint_as_float(o1[0]), so.x, so.y));
-    const bool mine = (lane >> 4) == pass16 && (lane & 15) < nv;
-    const unsigned surv = __ballot_sync(0xffffffffu, mine && obj32 >= P.conf);   // class scores are sigmoids (<= 1)
+    const unsigned surv = ibin_obj_survivors<LEN>(o1[0], tab_s, pass16, nv, P.conf, lane);
+    fused_epilogue_ibin_half_tail<LEN, PAIR>(P, L, b, prow0, nv, ar, tq, pass16, tab_s, qrow_s, tempty, lane, surv);
+}
+
+// the rest of fused_epilogue_ibin_half once the survivors are known (the CTA-pair kernel probes the objectness of all
+// anchors of a tile behind one wait and then comes here anchor by anchor).
+// A survivor's row is decoded by the WHOLE warp: the two lanes that hold it park its 127 raw accumulators in the warp's
+// row buffer, then the 32 lanes spread over the columns -- three classes, one w bin and one h bin each -- and the three
+// arg-maxes are warp reductions (first maximum: larger value wins, ties go to the smaller index, as torch.max).  ~300
+// instructions per survivor row; the per-thread form (every lane runs the 64 sigmoids of its half row and the bin scan
+// for all 16 rows of the warp) took ~1800 at a third of an instruction per cycle, longer than a tile's MMAs, so that a
+// warp with a survivor came late to the next tile: 224 -> 133 us per 16 images at 1280x1280 without that path.
+template <int LEN, bool PAIR>
+__device__ __forceinline__ void fused_epilogue_ibin_half_tail(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar,
+                                                              uint32_t tq, int pass16, uint32_t tab_s, uint32_t qrow_s, uint64_t *tempty,
+                                                              int lane, unsigned surv)
+{
+    constexpr int OFF = 64, C_OBJ = 2 + 2 * LEN, C_CLS = C_OBJ + 1;
+    const int no = P.no, nc = no - C_CLS;
+    const int half = lane >> 4, cbase = half * OFF;
     uint32_t v[OFF];
     if (surv) {
         TmemLdHalf<64, OFF>::ld(tq + ((uint32_t)(16 * pass16) << 16), v);
@@ -793,58 +825,81 @@ __device__ __forceinline__ void fused_epilogue_ibin_half(const TcParams &P, cons
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty);
+    if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(tempty);
+        else mbar_arrive(tempty);
+    }
     if (!surv) return;
-    const uint32_t trow = tab_s + (uint32_t)cbase * 8u;
-    // objectness of row r (lower lanes) and the class maximum of this thread's class columns, ascending
-    const float2 sob = lds_f32x2(trow + 8u * C_OBJ);
-    const float obj = sigmoidf_fast(fmaf(__uint_as_float(v[C_OBJ]), sob.x, sob.y));
-    float bv = -1.0f;
-    int best = 0;
+    float *const q = shared_f32(qrow_s);   // [128] raw accumulators of the row being decoded
+    // (scale, bias) applied, sigmoid: column c of the parked row
+    auto sig = [&](int c) {
+        const float2 s_b = lds_f32x2(tab_s + 8u * c);
+        return sigmoidf_fast(fmaf(q[c], s_b.x, s_b.y));
+    };
+    unsigned rows = (surv >> (16 * pass16)) & 0xFFFFu;   // survivors among this warp's 16 rows
+    while (rows) {
+        const int rr = __ffs(rows) - 1;
+        rows &= rows - 1;
+        if ((lane & 15) == rr) {   // lanes rr (columns 0..63) and rr + 16 (columns 64..127)
 #pragma unroll
-    for (int j = 0; j < OFF; ++j) {
-        const float2 s_b = lds_f32x2(trow + 8u * j);
-        float sg = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
-        if (j <= C_OBJ) sg = half != 0 ? sg : -1.0f;      // lower lanes: box part / objectness, not a class
-        if (j >= ncols) sg = -1.0f;                        // past the row (upper lanes)
-        if (sg > bv) { bv = sg; best = cbase + j - C_CLS; }
-    }
-    {   // row r: lower lane holds classes [0, 64 - C_CLS), lane r + 16 the rest (larger indices: ties stay with the lower lane)
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, 16);
-        const int oi = __shfl_xor_sync(0xffffffffu, best, 16);
-        if (ov > bv) { bv = ov; best = oi; }
-    }
-    const float score = __fmul_rn(obj, bv);
-    const bool pass = half == 0 && r < nv && obj >= P.conf && score >= P.conf;
-    if (!__ballot_sync(0xffffffffu, pass)) return;
-    // box of the lower lanes' rows: x y | w: reg + bins | h: reg + bins (same operations as store_rows_half_ibin)
-    const int p = prow0 + r;
-    float bx[2], reg_w = 0.f, reg_h = 0.f, best_w = -1.f, best_h = -1.f;
-    int idx_w = 0, idx_h = 0;
+            for (int j = 0; j < OFF; ++j) q[cbase + j] = __uint_as_float(v[j]);
+        }
+        __syncwarp();
+        // class maximum: lane l scans the classes l, l + 32, l + 64 in ascending order
+        float bv = -1.0f;
+        int best = 0;
 #pragma unroll
-    for (int j = 0; j < C_OBJ; ++j) {
-        const float2 s_b = lds_f32x2(trow + 8u * j);
-        const float sg = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
-        if (j == 0) bx[0] = decode_xy(sg, (float)(p % L.nx), L.stride);
-        else if (j == 1) bx[1] = decode_xy(sg, (float)(p / L.nx), L.stride_y);
-        else if (j == 2) reg_w = sg;
-        else if (j < 2 + LEN) { if (sg > best_w) { best_w = sg; idx_w = j - 3; } }
-        else if (j == 2 + LEN) reg_h = sg;
-        else { if (sg > best_h) { best_h = sg; idx_h = j - 3 - LEN; } }
-    }
-    float wh[2];
+        for (int k3 = 0; k3 < 3; ++k3) {
+            const int k = lane + 32 * k3;
+            if (k < nc) {
+                const float sg = sig(C_CLS + k);
+                if (sg > bv) { bv = sg; best = k; }
+            }
+        }
 #pragma unroll
-    for (int d = 0; d < 2; ++d) {
-        float t = __fmul_rn(d == 0 ? reg_w : reg_h, 2.0f);
-        t = __fadd_rn(t, -1.0f);
-        t = __fmul_rn(t, P.bin_step);
-        float res = __fadd_rn(t, __ldg(P.bins + (d == 0 ? idx_w : idx_h)));
-        res = fminf(fmaxf(res, 0.0f), 4.0f);
-        wh[d] = __fmul_rn(res, L.anchor_wh[2 * ar + d]);
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, best, off);
+            if (ov > bv || (ov == bv && oi < best)) { bv = ov; best = oi; }
+        }
+        const float obj = sig(C_OBJ);
+        const float score = __fmul_rn(obj, bv);
+        if (obj >= P.conf && score >= P.conf) {   // warp-uniform
+            // bins: lane l < LEN - 1 holds bin l of the w block and of the h block
+            float bw = -1.0f, bh = -1.0f;
+            int iw = lane, ih = lane;
+            if (lane < LEN - 1) {
+                bw = sig(3 + lane);
+                bh = sig(3 + LEN + lane);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ow = __shfl_xor_sync(0xffffffffu, bw, off), oh = __shfl_xor_sync(0xffffffffu, bh, off);
+                const int jw = __shfl_xor_sync(0xffffffffu, iw, off), jh = __shfl_xor_sync(0xffffffffu, ih, off);
+                if (ow > bw || (ow == bw && jw < iw)) { bw = ow; iw = jw; }
+                if (oh > bh || (oh == bh && jh < ih)) { bh = oh; ih = jh; }
+            }
+            if (lane == 0) {
+                const int p = prow0 + rr;
+                const float cx = decode_xy(sig(0), (float)(p % L.nx), L.stride);
+                const float cy = decode_xy(sig(1), (float)(p / L.nx), L.stride_y);
+                float wh[2];
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {   // (reg * 2 - 1) * step + bins[argmax], clamped to [0, 4], times the anchor
+                    float t = __fmul_rn(sig(d == 0 ? 2 : 2 + LEN), 2.0f);
+                    t = __fadd_rn(t, -1.0f);
+                    t = __fmul_rn(t, P.bin_step);
+                    float res = __fadd_rn(t, __ldg(P.bins + (d == 0 ? iw : ih)));
+                    res = fminf(fmaxf(res, 0.0f), 4.0f);
+                    wh[d] = __fmul_rn(res, L.anchor_wh[2 * ar + d]);
+                }
+                float x1, y1, x2, y2;
+                xywh_to_corners(cx, cy, wh[0], wh[1], P.div_w, P.div_h, x1, y1, x2, y2);
+                emit_one(b, L.row_off + ar * L.HW + p, P.rows_total, P.nc, x1, y1, x2, y2, obj, bv, score, best, P.ws);
+            }
+        }
+        __syncwarp();   // the row buffer is free again
     }
-    float x1, y1, x2, y2;
-    xywh_to_corners(bx[0], bx[1], wh[0], wh[1], P.div_w, P.div_h, x1, y1, x2, y2);
-    emit_candidates(pass, b, L.row_off + ar * L.HW + p, P.rows_total, P.nc, x1, y1, x2, y2, obj, bv, score, best, P.ws);
 }
 
 // the OFF values instantiated (tcgen05.ld takes the half-split offset as an immediate)
