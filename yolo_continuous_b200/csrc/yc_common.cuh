@@ -95,6 +95,18 @@ __device__ __forceinline__ float sigmoidf_fast(float t)
     return r;
 }
 
+// The two-MUFU form (ex2 + rcp, five instructions instead of thirteen) for epilogues that are bound by instruction issue
+// rather than by the special-function pipe: the IBin half-row epilogues run two warps per scheduler (A/B on one box,
+// 16 images at 1280x1280: forward 254.7 -> 227.3 us; the IDetect forward with three warps per scheduler loses 3.5 %).
+// Every IBin path of one configuration uses the same form, so the fused step and the two-call path stay bit-identical.
+__device__ __forceinline__ float sigmoidf_rcp(float t)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+
 // xy = (s*2 - 0.5 + g) * stride, evaluated in the reference's operation order
 // (nets/idetect.py:41) with no fused multiply-add.
 __device__ __forceinline__ float decode_xy(float s, float g, float stride)

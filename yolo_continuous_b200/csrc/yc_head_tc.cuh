@@ -728,7 +728,7 @@ __device__ __forceinline__ void store_rows_half_ibin(const TcParams &P, const Tc
 #pragma unroll
             for (int j = j0; j < j0 + HG; ++j) {
                 const float2 s_b = lds_f32x2(trow + 8u * j);
-                w[j - j0] = sigmoidf_fast(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
+                w[j - j0] = sigmoidf_rcp(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
             }
 #pragma unroll
             for (int j = j0; j < j0 + HG; ++j) {
@@ -779,7 +779,7 @@ template <int LEN>
 __device__ __forceinline__ unsigned ibin_obj_survivors(uint32_t o_raw, uint32_t tab_s, int pass16, int nv, float conf, int lane)
 {
     const float2 so = lds_f32x2(tab_s + 8u * (2 + 2 * LEN));
-    const float obj32 = sigmoidf_fast(fmaf(__uint_as_float(o_raw), so.x, so.y));
+    const float obj32 = sigmoidf_rcp(fmaf(__uint_as_float(o_raw), so.x, so.y));
     const bool mine = (lane >> 4) == pass16 && (lane & 15) < nv;
     return __ballot_sync(0xffffffffu, mine && obj32 >= conf);
 }
@@ -834,7 +834,7 @@ __device__ __forceinline__ void fused_epilogue_ibin_half_tail(const TcParams &P,
     // (scale, bias) applied, sigmoid: column c of the parked row
     auto sig = [&](int c) {
         const float2 s_b = lds_f32x2(tab_s + 8u * c);
-        return sigmoidf_fast(fmaf(q[c], s_b.x, s_b.y));
+        return sigmoidf_rcp(fmaf(q[c], s_b.x, s_b.y));
     };
     unsigned rows = (surv >> (16 * pass16)) & 0xFFFFu;   // survivors among this warp's 16 rows
     while (rows) {
