@@ -1256,6 +1256,37 @@ def test_ibin_fused_step_equals_two_call_path(conf, iou, shapes, bs):
     assert torch.equal(r[0][:int(r[3][-1])], res[0][0]) and torch.equal(r[2], res[0][2])
 
 
+def test_ibin_pair_kernel_equals_one_cta_kernel_full_sizes(monkeypatch):
+    """IBin at the C5 feature-map sizes (160/80/40 maps, K = 256/512/1024, 5 images: every CTA pair walks several tiles of
+    the resident level and of the two streaming ones, the last tiles are partial): the CTA-pair kernel that reads the maps
+    once for all anchors (head_tc2i_kernel) against the 1-CTA kernel (one anchor per tile) -- same k order, same epilogue
+    code, so z, the raw maps and the fused step's detections are bit-identical."""
+    from yolo_continuous_b200.pipeline import PostBackbone
+    ch, shapes, bs = (256, 512, 1024), [(160, 160), (80, 80), (40, 40)], 5
+    head = _ibin_head(ch, 8).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    xs = [torch.randn(bs, c, h, w, generator=g, device=DEV).to(torch.bfloat16) for c, (h, w) in zip(ch, shapes)]
+    out = {}
+    for two_cta in ("1", "0"):
+        monkeypatch.setenv("YC_TC_2CTA", two_cta)
+        head.return_raw = True
+        z, raws = head(list(xs))
+        pipe = PostBackbone(head, bs, shapes, torch.bfloat16, (1280, 1280), (720, 1280), True, 0.25, 0.45, DEV, use_graph=False)
+        rows, idx, counts, offsets = pipe.run_device(xs)
+        assert pipe.fused and pipe.ibin
+        tot = int(offsets[-1])
+        out[two_cta] = (z, raws, rows[:tot].clone(), idx[:tot].clone(), counts.clone())
+        del pipe
+    a, b = out["1"], out["0"]
+    assert a[0].shape == (bs, 3 * (160 * 160 + 80 * 80 + 40 * 40), 85) and int(a[4].sum()) > 50
+    assert torch.equal(a[0], b[0])
+    for ra, rb in zip(a[1], b[1]):
+        assert torch.equal(ra, rb)
+    assert torch.equal(a[4], b[4])
+    # candidates are emitted in a different order by the two kernels; the NMS result is ordered by (class, score, row)
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+
+
 def test_ibin_fused_step_vs_oracle_pipeline():
     """IBin fused step against the oracle pipeline (head_forward('ibin') -> non_max_suppression) on bf16-representable
     inputs, with the threshold placed in a score gap and bin ties excluded by construction of the check."""
