@@ -543,7 +543,8 @@ __device__ __forceinline__ void store_epilogue(const TcParams &P, const TcLevel 
 // and the TMEM buffer goes back to the MMA warp as soon as the second pass is in registers; the slab is 16 rows (half
 // the shared memory: three stages instead of two); (scale, bias) come from a table in shared memory; the slab is
 // written with st.shared.
-constexpr int HG = 8;   // columns per group of independent sigmoids in store_rows_half
+constexpr int HG = 8;        // columns per group of independent sigmoids in store_rows_half (16: no change, 32: 5 % slower)
+constexpr int HG_IBIN = 16;  // ... in store_rows_half_ibin (two warps per scheduler: 8 -> 16 gains 4 %, 32 loses it again)
 template <int OFF>
 __device__ __forceinline__ void ld_half_row(uint32_t ta, uint32_t *v)
 {
@@ -700,15 +701,15 @@ __device__ __forceinline__ void store_rows_half_ibin(const TcParams &P, const Tc
         __syncwarp();
         float *const srow = shared_f32(slab_s) + r * no + cbase;
 #pragma unroll
-        for (int j0 = 0; j0 < OFF; j0 += HG) {
-            float w[HG];
+        for (int j0 = 0; j0 < OFF; j0 += HG_IBIN) {
+            float w[HG_IBIN];
 #pragma unroll
-            for (int j = j0; j < j0 + HG; ++j) {
+            for (int j = j0; j < j0 + HG_IBIN; ++j) {
                 const float2 s_b = lds_f32x2(trow + 8u * j);
                 w[j - j0] = fmaf(__uint_as_float(v[j]), s_b.x, s_b.y);
             }
 #pragma unroll
-            for (int j = j0; j < j0 + HG; ++j)
+            for (int j = j0; j < j0 + HG_IBIN; ++j)
                 *(j < ncols ? srow + j : dummy) = w[j - j0];
         }
         half_slab_store(L.raw + (((size_t)b * P.na_real + ar) * L.HW + prow0) * no, slab_s, rows, no, lane);
@@ -723,15 +724,15 @@ __device__ __forceinline__ void store_rows_half_ibin(const TcParams &P, const Tc
         float reg_w = 0.f, reg_h = 0.f, best_w = -1.f, best_h = -1.f;
         int idx_w = 0, idx_h = 0;
 #pragma unroll
-        for (int j0 = 0; j0 < OFF; j0 += HG) {
-            float w[HG];
+        for (int j0 = 0; j0 < OFF; j0 += HG_IBIN) {
+            float w[HG_IBIN];
 #pragma unroll
-            for (int j = j0; j < j0 + HG; ++j) {
+            for (int j = j0; j < j0 + HG_IBIN; ++j) {
                 const float2 s_b = lds_f32x2(trow + 8u * j);
                 w[j - j0] = sigmoidf_rcp(fmaf(__uint_as_float(v[j]), s_b.x, s_b.y));
             }
 #pragma unroll
-            for (int j = j0; j < j0 + HG; ++j) {
+            for (int j = j0; j < j0 + HG_IBIN; ++j) {
                 const float sg = w[j - j0];
                 if (j < C_OBJ) {
                     // lower half: box part (kept in registers); upper half: a class column
