@@ -74,21 +74,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// shared memory by 32-bit shared-window address (pointers derived from the dynamic shared array through integer
-// arithmetic lose their address space and compile to generic LD / ST)
-__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
-// A pointer the compiler KNOWS to be shared memory (dynamic shared array + byte offset): plain C++ stores through it
-// compile to st.shared and, unlike volatile asm statements, may be scheduled freely among the arithmetic.
+// Shared memory behind 32-bit shared-window addresses.  Pointers derived from the dynamic shared array through integer
+// arithmetic lose their address space and compile to generic LD / ST; volatile asm stores are kept in program order by the
+// compiler and serialise the arithmetic around them.  shared_f32 gives a pointer the compiler KNOWS to be shared memory
+// (dynamic shared array + byte offset): plain C++ stores through it compile to st.shared and are scheduled freely.
+// (Store unconditionally -- to a dummy word where a column does not exist: a C++ `if` around the store lets the compiler
+// sink the computation of the value into a divergent branch per column.)
 __device__ __forceinline__ float *shared_f32(uint32_t saddr)
 {
     extern __shared__ uint8_t yc_dyn_smem[];
     return (float *)(yc_dyn_smem + (saddr - smem_addr(yc_dyn_smem)));
-}
-// predicated form: the value is computed by every thread (a C++ `if` around the store lets the compiler sink the whole
-// computation of the value into a divergent branch per column, which serialises the columns)
-__device__ __forceinline__ void sts_f32_if(uint32_t saddr, float v, bool on)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}" ::"r"(saddr), "f"(v), "r"((uint32_t)on) : "memory");
 }
 __device__ __forceinline__ float2 lds_f32x2(uint32_t saddr)
 {
