@@ -181,7 +181,8 @@ struct NmsSmem {
     unsigned long long skeys[SORT_SMEM];
     float4 sbox[NMS_NT];
     float4 skept[KEPT_SMEM];
-    unsigned long long smask[NMS_NT][2];
+    unsigned long long smask[NMS_NT][2];    // IoU bits of row i against later boxes of the chunk (OR of two threads' parts)
+    unsigned char sdeadb[NMS_NT];           // box i of the chunk is suppressed by a box kept earlier
     unsigned int sdead[NMS_NT / 32];
     unsigned int sany[NMS_NT / 32];
     unsigned long long skeptw[2];
@@ -194,6 +195,7 @@ __device__ void nms_segment_cta(int b, int c, int n, int rows, int nc, float thr
     unsigned long long *skeys = sm.skeys;
     float4 *sbox = sm.sbox, *skept = sm.skept;
     unsigned long long(*smask)[2] = sm.smask;
+    unsigned char *sdeadb = sm.sdeadb;
     unsigned int *sdead = sm.sdead, *sany = sm.sany;
     unsigned long long *skeptw = sm.skeptw;
     int &s_nkept = sm.s_nkept;
@@ -244,27 +246,61 @@ __device__ void nms_segment_cta(int b, int c, int n, int rows, int nc, float thr
             sbox[tid] = bx;
         }
         const int nk = s_nkept;
+        sdeadb[tid] = tid >= m;
+        smask[tid][0] = 0;
+        smask[tid][1] = 0;
         __syncthreads();
-        bool dead = tid >= m;
-        if (!dead) {
-            for (int k = 0; k < nk; ++k) {
-                const float4 kb = k < KEPT_SMEM ? skept[k] : kept_box[k];
-                if (iou_gt(kb, bx, thr_f)) { dead = true; break; }
+        {   // chunk against the kept list: NMS_NT / 2^ceil(log2 m) threads share a box and stride over the kept boxes (a
+            // short last chunk against a long kept list is otherwise a handful of lanes walking it alone)
+            int mp = 1;
+            while (mp < m) mp <<= 1;
+            const int tpb = NMS_NT / mp, bi = tid / tpb, sub = tid - bi * tpb;
+            if (bi < m) {
+                const float4 bb = sbox[bi];
+                bool hit = false;
+                for (int k = sub; k < nk && !hit; k += tpb) {
+                    const float4 kb = k < KEPT_SMEM ? skept[k] : kept_box[k];
+                    hit = iou_gt(kb, bb, thr_f);
+                }
+                if (hit) sdeadb[bi] = 1;
             }
         }
-        unsigned long long m0 = 0, m1 = 0;
-        if (!dead) {
-            for (int j = tid + 1; j < m; ++j) {
-                if (iou_gt(bx, sbox[j], thr_f)) {
-                    if (j < 64) m0 |= 1ull << j;
-                    else m1 |= 1ull << (j - 64);
+        __syncthreads();
+        const bool dead = sdeadb[tid] != 0;
+        // upper-triangular IoU bits of the chunk, balanced: rows lo = min(t, m-1-t) and hi = m-1-lo have m - 1 columns
+        // between them; thread lo takes the first m / 2 columns of its row, thread hi the rest of row lo and all of its own
+        // row (the parts are OR-ed into smask atomically).  Every thread does ~m / 2 tests (the plain triangle: thread 0 does
+        // m - 1, the last one none).
+        unsigned long long m0 = 0, m1 = 0, p0 = 0, p1 = 0;
+        if (tid < m) {
+            const int part = m - 1 - tid, lo = min(tid, part), half = m >> 1;
+            if (!dead) {   // own row: columns (tid, m), or the first `half` of them for the lower thread of a pair
+                const int jend = (tid == lo && tid != part) ? tid + 1 + half : m;
+                for (int j = tid + 1; j < jend; ++j) {
+                    if (iou_gt(bx, sbox[j], thr_f)) {
+                        if (j < 64) m0 |= 1ull << j;
+                        else m1 |= 1ull << (j - 64);
+                    }
                 }
             }
+            if (tid != lo) {   // upper thread of a pair: the rest of row lo
+                if (!sdeadb[lo]) {
+                    const float4 bl = sbox[lo];
+                    for (int j = lo + 1 + half; j < m; ++j) {
+                        if (iou_gt(bl, sbox[j], thr_f)) {
+                            if (j < 64) p0 |= 1ull << j;
+                            else p1 |= 1ull << (j - 64);
+                        }
+                    }
+                }
+                if (p0) atomicOr(&smask[lo][0], p0);
+                if (p1) atomicOr(&smask[lo][1], p1);
+            }
+            if (m0) atomicOr(&smask[tid][0], m0);
+            if (m1) atomicOr(&smask[tid][1], m1);
         }
-        smask[tid][0] = m0;
-        smask[tid][1] = m1;
         const unsigned d = __ballot_sync(0xffffffffu, dead);
-        const unsigned any_mask = __ballot_sync(0xffffffffu, (m0 | m1) != 0ull);
+        const unsigned any_mask = __ballot_sync(0xffffffffu, (m0 | m1 | p0 | p1) != 0ull);
         if (lane == 0) { sdead[wid] = d; sany[wid] = any_mask; }
         __syncthreads();
         // kept set of this chunk as a 128-bit map (keptw): without intra-chunk overlaps it is simply the boxes
