@@ -157,10 +157,11 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, const flo
 {
     const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    // disjoint boxes (the vast majority of pairs): the quotient is +-0 or NaN, never above a non-negative threshold -- skip
+    // the extents, the two areas and the IEEE division.  w = max(0, xx2 - xx1) is 0 exactly when !(xx2 > xx1): the
+    // difference of two distinct floats is never 0 (gradual underflow), and NaN compares false / max(0, NaN) = 0
+    if (!(xx2 > xx1 && yy2 > yy1) && thr_f >= 0.0f) return false;
     const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
-    // disjoint boxes (the vast majority of pairs): the quotient is +-0 or NaN, never above a non-negative threshold --
-    // skip the two areas and the IEEE division
-    if ((w == 0.0f || h == 0.0f) && thr_f >= 0.0f) return false;
     const float inter = __fmul_rn(w, h);
     const float aa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
     const float ab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
@@ -258,10 +259,10 @@ __device__ void nms_segment_cta(int b, int c, int n, int rows, int nc, float thr
             if (bi < m) {
                 const float4 bb = sbox[bi];
                 bool hit = false;
-                for (int k = sub; k < nk && !hit; k += tpb) {
-                    const float4 kb = k < KEPT_SMEM ? skept[k] : kept_box[k];
-                    hit = iou_gt(kb, bb, thr_f);
-                }
+                const int nks = min(nk, KEPT_SMEM);   // kept boxes cached in shared memory, the rest in global memory
+                int k = sub;
+                for (; k < nks && !hit; k += tpb) hit = iou_gt(skept[k], bb, thr_f);
+                for (; k < nk && !hit; k += tpb) hit = iou_gt(kept_box[k], bb, thr_f);
                 if (hit) sdeadb[bi] = 1;
             }
         }
