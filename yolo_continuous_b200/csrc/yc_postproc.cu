@@ -214,19 +214,24 @@ __device__ void nms_segment_cta(int b, int c, int n, int rows, int nc, float thr
         K = skeys;
     }
     __syncthreads();
+    // (a thread takes comparator t of a step directly -- lower index i = t with a 0 bit inserted at the stride's position --
+    // instead of walking all elements and skipping the upper halves of the pairs: half the instructions)
+    int half_pairs = 1;
+    while (2 * half_pairs < n) half_pairs <<= 1;   // comparators per step of the padded network
     for (int k = 2; (k >> 1) < n; k <<= 1) {
-        for (int i = tid; i < n; i += NMS_NT) {
-            const int l = i ^ (k - 1);
-            if (l > i && l < n) {
+        const int h = k >> 1;
+        for (int t = tid; t < half_pairs; t += NMS_NT) {
+            const int i = ((t & ~(h - 1)) << 1) | (t & (h - 1)), l = i ^ (k - 1);
+            if (l < n) {
                 const unsigned long long a = K[i], d = K[l];
                 if (a > d) { K[i] = d; K[l] = a; }
             }
         }
         __syncthreads();
         for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int i = tid; i < n; i += NMS_NT) {
-                const int l = i ^ j;
-                if (l > i && l < n) {
+            for (int t = tid; t < half_pairs; t += NMS_NT) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                if (l < n) {
                     const unsigned long long a = K[i], d = K[l];
                     if (a > d) { K[i] = d; K[l] = a; }
                 }
