@@ -616,10 +616,8 @@ __device__ __forceinline__ void store_rows_half(const TcParams &P, const TcLevel
             if (lane == 0) bulk_wait_read0();   // the slab's previous store has been read out
             __syncwarp();
             if (pf) { const long long c = clock64(); pf[0] += c - c0_; c0_ = c; }
-            // (values first, stores after: the st.shared are volatile asm statements, which the compiler keeps in program
-            // order -- interleaved with the arithmetic they serialise every column behind the latency of the previous one)
-            // (HG values, then HG stores: the st.shared are volatile asm statements, which the compiler keeps in program order
-            // -- interleaved one by one with the arithmetic they serialise every column behind the latency of the previous one)
+            // groups of HG columns: HG independent values, then their stores (through shared_f32 pointers, which the compiler
+            // may schedule among the arithmetic; columns that do not exist go to the dummy word instead of a branch)
 #pragma unroll
             for (int j0 = 0; j0 < OFF; j0 += HG) {
                 float w[HG];
