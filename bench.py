@@ -758,6 +758,12 @@ def main():
     peaks, peak_src = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     bytes_launch = (BYTES_PER_IMG_FUSED if pipe.fused else BYTES_PER_IMG)[args.dtype] * args.bs
+    # The roofline figure is the head kernel timed ALONE (the single-stream pass: nothing else runs on the GPU while it
+    # does, which is also what the ncu capture sees); next to the NMS kernels of the previous batch (the pipelined step)
+    # the same launch takes ~10 % longer -- that duration is kept as kernel_ms_beside_nms and bounds the step.
+    head_beside_ms = head_ms
+    if serial_share:
+        head_ms = serial_share["head_ms"]
     achieved = bytes_launch / (head_ms / 1e3) / 1e9
     traffic = None
     try:
@@ -770,10 +776,13 @@ def main():
     roofline = {"kernel": kname,
                 "stage": "S3 fused head->candidates (z never written)" if pipe.fused else "S1 head->z",
                 "peak_source": peak_src, "traffic": traffic, "kernel_ms": head_ms,
-                "kernel_share_of_step": head_ms / (ms / K),
-                "kernel_timing": f"CUDA events around each launch in a second pass of the same {K} steps issued call by call "
-                                 f"({eager_ms / K:.4f} ms per step; the graph-replayed timed region above cannot hold "
-                                 f"per-kernel events)",
+                "kernel_ms_beside_nms": head_beside_ms,
+                "kernel_share_of_step": head_beside_ms / (ms / K),
+                "kernel_timing": "kernel_ms: CUDA events around each of 20 launches in a single-stream pass (the kernel alone "
+                                 "on the GPU, the NMS kernels after it); kernel_ms_beside_nms: the same around each launch of "
+                                 f"a second pass of the {K} steps issued call by call on two streams ({eager_ms / K:.4f} ms per "
+                                 "step), where the NMS kernels of the previous batch share the SMs with it, as in the "
+                                 "graph-replayed timed region (which cannot hold per-kernel events)",
                 # the three NMS kernels of a step, timed on their own stream (they run next to the NEXT step's head
                 # kernel when pipelined, which stretches them); kernel_share_serialised comes from a single-stream
                 # pass of 20 steps and is what an ncu launch list (serialised) shows
