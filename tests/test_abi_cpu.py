@@ -129,3 +129,35 @@ def test_product_never_touches_the_oracle_or_the_reference():
     assert not bad, bad
     for f in glob.glob(os.path.join(root, "yolo_continuous_b200", "csrc", "*.cu*")):
         assert "oracle" not in open(f).read().lower().replace("oracle computes", ""), f
+
+
+def test_half_split_offsets_stay_inside_the_accumulator(tmp_path):
+    """Host logic of the half-row z epilogue (csrc/yc_head_tc.cuh, half_off_for): for every head shape the offset it picks
+    lets lanes 16-31 read the columns [OFF, 2 OFF) of the LAST anchor of a tile without leaving the 256-column TMEM buffer,
+    covers the row (2 OFF >= no) and is one of the instantiated values; shapes it declines fall back to the whole-row
+    epilogue.  Compiled with nvcc as host code: no GPU needed."""
+    src = tmp_path / "off.cu"
+    src.write_text(r'''
+#include <cstdio>
+#include "yc_head_tc.cuh"
+int main() {
+  int bad = 0, taken = 0;
+  for (int na = 1; na <= 4; ++na)
+    for (int no = 6; no <= 256; ++no) {
+      if (na * no > 256) continue;              // all anchors in one tile, as launch_head_tcgen05 requires
+      const int off = yc::half_off_for(no, na);
+      if (!off) continue;
+      ++taken;
+      const bool inst = off == 4 || off == 8 || off == 16 || off == 32 || off == 43 || off == 64;
+      if (!inst || 2 * off < no || off > no || (na - 1) * no + 2 * off > 256) { printf("bad: na %d no %d off %d\n", na, no, off); ++bad; }
+    }
+  // the shapes of the shipped heads take the half-row path
+  if (yc::half_off_for(85, 3) != 43 || yc::half_off_for(6, 3) != 4 || yc::half_off_for(25, 3) != 16 || yc::half_off_for(127, 1) != 64) ++bad;
+  printf("%d %d\n", bad, taken);
+  return 0; }''')
+    exe = tmp_path / "off"
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
+                           "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "yolo_continuous_b200", "csrc"),
+                           str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert int(out[-2]) == 0 and int(out[-1]) > 300, out
