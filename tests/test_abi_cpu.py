@@ -161,3 +161,45 @@ int main() {
                            str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)], text=True).split()
     assert int(out[-2]) == 0 and int(out[-1]) > 300, out
+
+
+def test_chunked_tile_order_visits_every_tile_once(tmp_path):
+    """Host check of tile_coord_w (csrc/yc_head_tc.cuh): the tile order of heads with one anchor group per tile -- group major
+    inside chunks of pixel tiles, the last chunk short -- is a permutation of (level, image, pixel tile, group)."""
+    src = tmp_path / "order.cu"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <tuple>
+#include "yc_head_tc.cuh"
+int main() {
+  int bad = 0;
+  const int chunks[] = {1, 7, 148, 296, 100000};
+  for (int bs = 1; bs <= 5; bs += 2)
+    for (int ci = 0; ci < 5; ++ci) {
+      yc::TcParams P;
+      memset(&P, 0, sizeof(P));
+      P.n_lv = 3; P.bs = bs;
+      const int hw[3] = {400, 1600, 6400};
+      int tiles = 0;
+      for (int l = 0; l < 3; ++l) {
+        P.lv[l].HW = hw[l]; P.lv[l].tiles_per_img = (hw[l] + 127) / 128; P.lv[l].n_groups = 3; P.lv[l].chunk_tiles = chunks[ci];
+        P.lv[l].tile_begin = tiles; tiles += bs * P.lv[l].tiles_per_img * 3;
+      }
+      P.total_tiles = tiles;
+      std::set<std::tuple<int, int, int, int>> seen;
+      for (int t = 0; t < tiles; ++t) {
+        const yc::TileCoord c = yc::tile_coord_w(P, t, 128);
+        if (c.lv < 0 || c.lv > 2 || c.g < 0 || c.g > 2 || c.b < 0 || c.b >= bs || c.p0 < 0 || c.p0 >= hw[c.lv] || c.p0 % 128) ++bad;
+        seen.insert(std::make_tuple(c.lv, c.b, c.p0, c.g));
+      }
+      if ((int)seen.size() != tiles) ++bad;
+    }
+  printf("%d\n", bad);
+  return 0; }''')
+    exe = tmp_path / "order"
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
+                           "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "yolo_continuous_b200", "csrc"),
+                           str(src), "-o", str(exe)])
+    assert subprocess.check_output([str(exe)], text=True).split()[-1] == "0"

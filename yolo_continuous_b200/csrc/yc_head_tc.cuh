@@ -94,7 +94,7 @@ struct TcMaps {
 struct TileCoord { int lv, b, p0, g; };
 
 // tile id -> (level, image, first pixel, anchor group); `width` = pixels per tile (128, or 256 for a CTA pair)
-__device__ __forceinline__ TileCoord tile_coord_w(const TcParams &P, int t, int width)
+__host__ __device__ __forceinline__ TileCoord tile_coord_w(const TcParams &P, int t, int width)
 {
     int l = 0;
 #pragma unroll
