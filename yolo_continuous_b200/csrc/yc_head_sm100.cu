@@ -245,9 +245,14 @@ head_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
             if (IBIN && P.half_off) {   // eight warps: (quadrant, half of its rows)
                 const int pass = e >> 2;
-                store_rows_half_ibin<22, false>(P, L, tc.b, prow0 + 16 * pass, nv - 16 * pass, ar, taddr + ((uint32_t)(16 * pass) << 16),
-                                         smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no), smem_addr(slab), smem_addr(bars + 16),
-                                         &tempty_bar[buf], lane);
+                if (P.no >= 127)
+                    store_rows_half_ibin<22, false, true>(P, L, tc.b, prow0 + 16 * pass, nv - 16 * pass, ar, taddr + ((uint32_t)(16 * pass) << 16),
+                                                          smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no), smem_addr(slab),
+                                                          smem_addr(bars + 16), &tempty_bar[buf], lane);
+                else
+                    store_rows_half_ibin<22, false, false>(P, L, tc.b, prow0 + 16 * pass, nv - 16 * pass, ar, taddr + ((uint32_t)(16 * pass) << 16),
+                                                           smem_addr(sbtab + (tc.lv * P.na_real + ar) * P.no), smem_addr(slab),
+                                                           smem_addr(bars + 16), &tempty_bar[buf], lane);
                 continue;
             }
             if (!IBIN && P.half_off) {

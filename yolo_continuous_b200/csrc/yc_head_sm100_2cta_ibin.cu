@@ -284,9 +284,12 @@ head_tc2i_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
                 const uint32_t tab_s = smem_addr(sbtab + (tc.lv * P.na_real + g) * P.no);
                 if (FUSED)
                     fused_epilogue_ibin_half<22, true>(P, L, img, prow0, nv, g, taddr, pass16, tab_s, slab_s, &tempty[slot], lane);
+                else if (P.no >= 127)
+                    store_rows_half_ibin<22, true, true>(P, L, img, prow0, nv, g, taddr + ((uint32_t)(16 * pass16) << 16), tab_s, slab_s,
+                                                         dummy_s, &tempty[slot], lane);
                 else
-                    store_rows_half_ibin<22, true>(P, L, img, prow0, nv, g, taddr + ((uint32_t)(16 * pass16) << 16), tab_s, slab_s,
-                                                   dummy_s, &tempty[slot], lane);
+                    store_rows_half_ibin<22, true, false>(P, L, img, prow0, nv, g, taddr + ((uint32_t)(16 * pass16) << 16), tab_s, slab_s,
+                                                          dummy_s, &tempty[slot], lane);
             }
         }
         if (!FUSED && lane == 0) bulk_wait_all0();   // global writes complete before the CTA exits

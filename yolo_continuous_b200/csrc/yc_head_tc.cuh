@@ -673,7 +673,9 @@ __device__ __forceinline__ void store_rows_half(const TcParams &P, const TcLevel
 // thread; the bin arg-max (first maximum of the sigmoids, as torch.max) runs in registers of the lower half-warp.
 // The whole-row form (three warps per quadrant sharing the columns, 16-column chunks, branches on the column's role with
 // a run-time LEN) took 186-226 cycles per box column and warp (YC_TC_DEBUG bit 8).
-template <int LEN, bool PAIR>
+// TAIL1: no >= 127, so only the very last column of the upper half (accumulator column 127) can be missing: the stores of all
+// other columns need no dummy-word select
+template <int LEN, bool PAIR, bool TAIL1>
 __device__ __forceinline__ void store_rows_half_ibin(const TcParams &P, const TcLevel &L, int b, int prow0, int nv, int ar,
                                                      uint32_t taddr, uint32_t tab_s, uint32_t slab_s, uint32_t dummy_s, uint64_t *tempty, int lane)
 {
@@ -708,7 +710,7 @@ __device__ __forceinline__ void store_rows_half_ibin(const TcParams &P, const Tc
             }
 #pragma unroll
             for (int j = j0; j < j0 + HG_IBIN; ++j)
-                *(j < ncols ? srow + j : dummy) = w[j - j0];
+                *(((TAIL1 && j < OFF - 1) || j < ncols) ? srow + j : dummy) = w[j - j0];
         }
         half_slab_store(L.raw + (((size_t)b * P.na_real + ar) * L.HW + prow0) * no, slab_s, rows, no, lane);
     }
@@ -742,10 +744,10 @@ __device__ __forceinline__ void store_rows_half_ibin(const TcParams &P, const Tc
                         const float d = j == 0 ? decode_xy(sg, gx, L.stride) : decode_xy(sg, gy, L.stride_y);
                         *(half == 0 ? srow + j : (j < ncols ? scol + j : dummy)) = half == 0 ? d : sg;
                     } else {
-                        *(half != 0 && j < ncols ? scol + j : dummy) = sg;
+                        *(half != 0 && ((TAIL1 && j < OFF - 1) || j < ncols) ? scol + j : dummy) = sg;
                     }
                 } else {
-                    *(j < ncols ? scol + j : dummy) = sg;
+                    *(((TAIL1 && j < OFF - 1) || j < ncols) ? scol + j : dummy) = sg;
                 }
             }
         }
